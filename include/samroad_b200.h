@@ -1,0 +1,134 @@
+/* samroad_b200.h -- C ABI of libsamroad_b200.so
+ *
+ * B200-native (sm_100a) implementation of the tiled-inference hot path of htcr/sam_road.
+ * Every entry point replaces one piece of the reference's Python interface (file:line cited per
+ * function, relative to the reference repository root).  The reference has no FFI of its own (it is
+ * pure PyTorch); the binding a maintainer adds is the ctypes stub shown in
+ * INTEGRATION.md, which is also what sam_road_b200/_lib.py implements.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *   - every function returns 0 on success; on failure a non-zero code is returned and
+ *     samroad_last_error() (thread-local) describes the problem.  Nothing throws or aborts.
+ *   - device pointers are caller-owned (e.g. torch tensors' data_ptr()); the handle owns only the
+ *     packed weights and its activation workspace.
+ *   - calls are asynchronous and ordered on the given cudaStream_t (passed as void*); one handle
+ *     per device, not re-entrant on the same handle.  Multi-GPU = one process per GPU.
+ *   - there is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef SAMROAD_B200_H_
+#define SAMROAD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAMROAD_ABI_VERSION 1
+
+typedef struct samroad_ctx* samroad_handle_t;
+
+/* dtype codes for polymorphic inputs */
+enum { SAMROAD_F32 = 0, SAMROAD_I64 = 1, SAMROAD_I32 = 2, SAMROAD_U8 = 3 };
+
+/* TOPONET_VERSION (model.py:84,111-116,135).  'no_tgt_features' behaves as 'normal' in the
+ * reference because the following if/else overwrites it (model.py:111-116). */
+enum { SAMROAD_TOPO_NORMAL = 0, SAMROAD_TOPO_NO_OFFSET = 1, SAMROAD_TOPO_NO_TRANSFORMER = 2 };
+
+/* Model hyper-parameters: what SAMRoad.__init__ derives from the YAML config (model.py:193-300). */
+typedef struct SamRoadCfg {
+  int32_t patch_size;             /* PATCH_SIZE: tile side in pixels, multiple of 16            */
+  int32_t embed_dim;              /* 768 (vit_b) / 1024 (vit_l) / 1280 (vit_h)  model.py:198-218 */
+  int32_t depth;                  /* 12 / 24 / 32                                               */
+  int32_t num_heads;              /* 12 / 16 / 16                                               */
+  int32_t window_size;            /* 14 (model.py:256)                                          */
+  int32_t global_attn_indexes[4]; /* model.py:203,210,217                                       */
+  int32_t use_sam_decoder;        /* USE_SAM_DECODER (model.py:260)                             */
+  int32_t toponet_version;        /* SAMROAD_TOPO_*                                             */
+  int32_t lora_rank;              /* 0 = no LoRA; else LORA_RANK (model.py:304-347)             */
+} SamRoadCfg;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+
+/* Replaces SAMRoad.__init__ + .to(device) (model.py:193-300, inferencer.py:247-254). */
+int samroad_create(const SamRoadCfg* cfg, int device, samroad_handle_t* out);
+int samroad_destroy(samroad_handle_t h);
+
+/* Replaces load_state_dict (inferencer.py:250-252): hand over one fp32 tensor of the reference's
+ * state_dict by its key (SURVEY.md §8b lists the key set) from HOST memory.  Unknown keys are an
+ * error.  After all tensors are loaded call samroad_finalize_weights(), which packs them to the
+ * device formats (fp16 K-major GEMM operands, LoRA merged into qkv, ConvTranspose re-ordered as
+ * GEMM) and reports any missing key. */
+int samroad_load_tensor(samroad_handle_t h, const char* key, const float* host_data,
+                        const int64_t* shape, int ndim);
+int samroad_finalize_weights(samroad_handle_t h);
+
+/* ---- the hot path --------------------------------------------------------------------------- */
+
+/* SAMRoad.infer_masks_and_img_features (model.py:459-495) and the mask half of forward()
+ * (model.py:414-446).  rgb: device [B,P,P,3], SAMROAD_F32 (0..255) or SAMROAD_U8.
+ * Outputs (device, fp32): mask_scores [B,P,P,2] (may be NULL), mask_logits [B,P,P,2] (may be NULL),
+ * image_embeddings [B,256,P/16,P/16]. */
+int samroad_encode_masks(samroad_handle_t h, const void* rgb, int rgb_dtype, int B,
+                         float* mask_scores, float* mask_logits, float* image_embeddings,
+                         void* stream);
+
+/* SAMRoad.infer_toponet (model.py:498-508) = BilinearSampler (model.py:34-58) + TopoNet.forward
+ * (model.py:88-148).  image_embeddings: device fp32 [B,256,s,s]; points [B,N,2] (x,y) pixels,
+ * SAMROAD_F32 / I64 / I32; pairs [B,Ns,Np,2] indices into N, SAMROAD_I64 / I32; valid [B,Ns,Np]
+ * bytes (0/1).  Outputs fp32 [B,Ns,Np] (either may be NULL).  Slots masked by `valid` report
+ * output_proj.bias, mirroring torch's eval fast path. */
+int samroad_toponet(samroad_handle_t h, const float* image_embeddings, const void* points,
+                    int pts_dtype, const void* pairs, int pairs_dtype, const uint8_t* valid, int B,
+                    int N, int Ns, int Np, float* topo_logits, float* topo_scores, void* stream);
+
+/* Mask fusion of inferencer.py:79-110: scores device fp32 [n_tiles,P,P,2] in tile-list order,
+ * tile origins (device int32) -> uint8 [H,W] keypoint and road masks (device). */
+int samroad_fuse_masks(const float* scores, int n_tiles, int P, const int32_t* tile_x0,
+                       const int32_t* tile_y0, int H, int W, uint8_t* keypoint_u8,
+                       uint8_t* road_u8, void* stream);
+
+/* Same as samroad_encode_masks but with HOST buffers (pinned or pageable): uploads the uint8 / fp32
+ * tiles, runs the path, downloads the results and synchronises.  This is the end-to-end call the
+ * benchmark's `e2e` figure times.  Any output pointer may be NULL. */
+int samroad_encode_masks_host(samroad_handle_t h, const void* rgb_host, int rgb_dtype, int B,
+                              float* mask_scores_host, float* image_embeddings_host);
+
+/* Activation workspace the handle needs for a batch of B tiles (bytes). */
+size_t samroad_workspace_bytes(samroad_handle_t h, int B);
+
+/* Number of kernels launched by this library since the last call with reset != 0. */
+uint64_t samroad_launch_count(int reset);
+
+const char* samroad_last_error(void);
+int samroad_abi_version(void);
+
+/* ---- op-level entry points (unit tests and composition; all pointers device, fp16 = IEEE half) ---- */
+
+/* out16[M,N] = act(A[M,K] W[N,K]^T + bias)      act: 0 none, 1 GELU(erf), 2 ReLU */
+int samroad_op_gemm_f16(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
+                        const float* bias, int act, void* out16, int ldo, void* stream);
+/* out32[M,N] = A W^T + bias + resid + pos[m % pos_rows]   (bias/resid/pos may be NULL) */
+int samroad_op_gemm_f32(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
+                        const float* bias, const float* resid, const float* pos, int pos_rows,
+                        float* out32, int ldo, void* stream);
+/* grouped LayerNorm epilogue, see gemm_tc.cuh EpiLN */
+int samroad_op_gemm_ln(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
+                       const float* bias, const float* resid, const float* gamma,
+                       const float* beta, float eps, int group, int act, void* out16, float* out32,
+                       float* out_nchw, int tokens, int ldo, void* stream);
+/* independent SIMT checker GEMM: out32 = A W^T */
+int samroad_op_gemm_ref(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
+                        float* out32, int ldo, void* stream);
+int samroad_op_layernorm(const float* x, const float* gamma, const float* beta, float eps, int M,
+                         int D, void* out16, void* stream);
+int samroad_op_attention(const void* qkv16, const float* qkv_bias, const float* rel_h,
+                         const float* rel_w, int B, int s, int win, int heads, int head_dim,
+                         void* out16, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAMROAD_B200_H_ */

@@ -1,0 +1,82 @@
+// sam_road_b200 :: host-side common pieces: last-error slot, SM count, TMA descriptor encoding.
+#include "common.cuh"
+#include "ops.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+
+namespace srb {
+
+static thread_local char g_last_error[1024] = "";
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+}
+const char* get_last_error() { return g_last_error; }
+
+static std::atomic<uint64_t> g_launches{0};
+void note_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
+uint64_t launch_count(bool reset) {
+  return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
+int device_sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      return 148;
+    cached = n;
+  }
+  return cached;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                     uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols) {
+  PFN_encodeTiled fn = get_encode_fn();
+  SRB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled driver entry point not available");
+  SRB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15u) == 0, "TMA base %p not 16-byte aligned",
+              base);
+  SRB_REQUIRE((ld_elems * 2) % 16 == 0, "TMA row pitch %llu B not a multiple of 16",
+              (unsigned long long)(ld_elems * 2));
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SRB_REQUIRE(r == CUDA_SUCCESS,
+              "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=%ux%u", (int)r,
+              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems,
+              box_rows, box_cols);
+  return 0;
+}
+
+}  // namespace srb

@@ -1,0 +1,77 @@
+// sam_road_b200 :: GEMM instantiations and tile-shape dispatch.
+#include "gemm_tc.cuh"
+#include "ops.h"
+
+namespace srb {
+
+// 128x256 tiles (4-stage ring, all 512 TMEM columns) when N allows and the grid still fills the GPU,
+// otherwise 128x128 tiles (6-stage ring).
+static inline bool use_bn256(int M, int N) {
+  if (N % 256 != 0) return false;
+  const long tiles256 = static_cast<long>((M + kGemmBM - 1) / kGemmBM) * (N / 256);
+  return tiles256 >= device_sm_count();
+}
+
+int gemm_f16out(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K,
+                const float* bias, int act, __half* out, int ldo, cudaStream_t st) {
+  EpiF16::Params p{out, bias, ldo, act};
+  SRB_REQUIRE(ldo % 8 == 0, "gemm_f16out: ldo=%d must be a multiple of 8", ldo);
+  if (use_bn256(M, N)) return launch_gemm_tc<256, 4, EpiF16>(A, lda, W, ldw, M, N, K, p, st);
+  return launch_gemm_tc<128, 6, EpiF16>(A, lda, W, ldw, M, N, K, p, st);
+}
+
+int gemm_f32out(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K,
+                const float* bias, const float* resid, const float* pos, int pos_rows, float* out,
+                int ldo, cudaStream_t st) {
+  EpiF32::Params p{out, bias, resid, pos, ldo, pos_rows > 0 ? pos_rows : 1, N};
+  SRB_REQUIRE(ldo % 4 == 0, "gemm_f32out: ldo=%d must be a multiple of 4", ldo);
+  if (use_bn256(M, N)) return launch_gemm_tc<256, 4, EpiF32>(A, lda, W, ldw, M, N, K, p, st);
+  return launch_gemm_tc<128, 6, EpiF32>(A, lda, W, ldw, M, N, K, p, st);
+}
+
+int gemm_ln(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K,
+            const float* bias, const float* resid, const float* gamma, const float* beta, float eps,
+            int group, int act, __half* out16, float* out32, float* out_nchw, int tokens, int ldo,
+            cudaStream_t st) {
+  SRB_REQUIRE(group == 128 || group == 256, "gemm_ln: group=%d must be 128 or 256", group);
+  SRB_REQUIRE(N % group == 0, "gemm_ln: N=%d not a multiple of group=%d", N, group);
+  EpiLN::Params p{out16, out32, out_nchw, bias, resid, gamma, beta, eps, ldo, group, act,
+                  tokens > 0 ? tokens : 1, N};
+  if (group == 256 || use_bn256(M, N))
+    return launch_gemm_tc<256, 4, EpiLN>(A, lda, W, ldw, M, N, K, p, st);
+  return launch_gemm_tc<128, 6, EpiLN>(A, lda, W, ldw, M, N, K, p, st);
+}
+
+int gemm_dec_final(const __half* A, int lda, const __half* W, int ldw, int M, int K,
+                   const float* bias3, const float* w4, const float* bias4, int s, int P,
+                   float* scores, float* logits, cudaStream_t st) {
+  EpiDecFinal::Params p{scores, logits, bias3, w4, bias4, s, P};
+  return launch_gemm_tc<128, 6, EpiDecFinal>(A, lda, W, ldw, M, 128, K, p, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// test-only checker: one thread per output element, fp32 FMA chain over K
+// ------------------------------------------------------------------------------------------------
+__global__ void gemm_ref_simt_kernel(const __half* __restrict__ A, int lda,
+                                     const __half* __restrict__ W, int ldw, int M, int N, int K,
+                                     float* __restrict__ out, int ldo) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (n >= N || m >= M) return;
+  const __half* a = A + static_cast<size_t>(m) * lda;
+  const __half* w = W + static_cast<size_t>(n) * ldw;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) acc = fmaf(__half2float(a[k]), __half2float(w[k]), acc);
+  out[static_cast<size_t>(m) * ldo + n] = acc;
+}
+
+int gemm_ref_simt(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K,
+                  float* out, int ldo, cudaStream_t st) {
+  dim3 grid((N + 127) / 128, M);
+  gemm_ref_simt_kernel<<<grid, 128, 0, st>>>(A, lda, W, ldw, M, N, K, out, ldo);
+  SRB_CUDA_OK(cudaGetLastError());
+  note_launch();
+  return 0;
+}
+
+}  // namespace srb

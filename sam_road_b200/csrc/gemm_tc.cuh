@@ -1,0 +1,493 @@
+// sam_road_b200 :: tcgen05 GEMM  C[M,N] = A[M,K] * W[N,K]^T  (+ fused epilogue)
+//
+// One kernel template covers every dense contraction of the hot path (SURVEY.md §2.4 K2, K5, K9,
+// K10, K11, K12, K16): fp16 operands (both K-major), fp32 accumulation in TMEM.
+//
+//   warp 0      : TMA producer   (cp.async.bulk.tensor, 128B-swizzled 128x64 / BNx64 boxes)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16)
+//   warps 2..5  : epilogue       (tcgen05.ld 32x32b -> registers -> fused math -> global)
+//
+// Persistent CTAs (grid = min(#tiles, #SMs)), STAGES-deep smem ring between TMA and MMA, and a
+// two-deep TMEM accumulator ring between MMA and epilogue so the epilogue of tile i overlaps the
+// main loop of tile i+1.  Tile order is n-fastest so the CTAs running concurrently share the same
+// A rows (L2 reuse); the weights (<= 4.7 MB per layer) stay L2-resident.
+//
+// Reference semantics implemented by the epilogues:
+//   nn.Linear (+bias)                       image_encoder.py:212-213,227,238; common.py:21-26
+//   GELU(erf)                               common.py:18-26, model.py:285
+//   x + pos_embed, shortcut + x             image_encoder.py:108-109,179-180
+//   LayerNorm2d (biased var, eps in sqrt)   common.py:31-43
+//   nn.LayerNorm post-norm (TopoNet)        model.py:74-85 (torch TransformerEncoderLayer)
+//   ConvTranspose2d(k=2,s=2) as GEMM        model.py:286-295
+#pragma once
+
+#include "common.cuh"
+#include "ops.h"
+
+namespace srb {
+
+constexpr int kGemmBM = 128;
+constexpr int kGemmBK = 64;
+constexpr int kGemmThreads = 192;
+
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == ACT_GELU) return gelu_erf_fast(x);
+  if (act == ACT_RELU) return fmaxf(x, 0.0f);
+  if (act == ACT_SIGMOID) return sigmoidf_(x);
+  return x;
+}
+
+// One accumulator row (this thread's TMEM lane) of the current tile.
+struct TmemRow {
+  uint32_t taddr;
+  __device__ __forceinline__ void load(int chunk, float (&v)[32]) const {
+    uint32_t r[32];
+    tmem_ld_32x32(taddr + static_cast<uint32_t>(chunk) * 32u, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue 1: out16[m,n] = act(acc + bias[n])                       (qkv, MLP lin1, TopoNet lin)
+// ------------------------------------------------------------------------------------------------
+struct EpiF16 {
+  struct Params {
+    __half* out;          // [M, ldo]
+    const float* bias;    // [N] or null
+    int ldo;
+    int act;
+  };
+  static __device__ __forceinline__ void run(const Params& p, int m, bool valid, int n_base,
+                                             int n_cols, const TmemRow& row) {
+    const int nchunks = n_cols >> 5;
+    for (int c = 0; c < nchunks; ++c) {
+      float v[32];
+      row.load(c, v);
+      const int n0 = n_base + c * 32;
+      if (p.bias) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 b = __ldg(b4 + i);
+          v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+        }
+      }
+      if (p.act != ACT_NONE) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
+      }
+      if (valid) {
+        uint4* o = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(m) * p.ldo + n0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 u;
+          u.x = pack_half2(v[8 * i + 0], v[8 * i + 1]);
+          u.y = pack_half2(v[8 * i + 2], v[8 * i + 3]);
+          u.z = pack_half2(v[8 * i + 4], v[8 * i + 5]);
+          u.w = pack_half2(v[8 * i + 6], v[8 * i + 7]);
+          o[i] = u;
+        }
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue 2: out32[m,n] = acc + bias[n] + resid[m,n] + pos[m % pos_rows, n]
+//             (patch-embed + pos_embed, attention proj + shortcut, MLP lin2 + shortcut; plain f32)
+// ------------------------------------------------------------------------------------------------
+struct EpiF32 {
+  struct Params {
+    float* out;           // [M, ldo]
+    const float* bias;    // [N] or null
+    const float* resid;   // [M, ldo] or null (may alias out)
+    const float* pos;     // [pos_rows, N] or null
+    int ldo;
+    int pos_rows;
+    int n_total;
+  };
+  static __device__ __forceinline__ void run(const Params& p, int m, bool valid, int n_base,
+                                             int n_cols, const TmemRow& row) {
+    const int nchunks = n_cols >> 5;
+    const float* posrow =
+        p.pos ? p.pos + static_cast<size_t>(m % p.pos_rows) * p.n_total : nullptr;
+    for (int c = 0; c < nchunks; ++c) {
+      float v[32];
+      row.load(c, v);
+      const int n0 = n_base + c * 32;
+      if (p.bias) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 b = __ldg(b4 + i);
+          v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+        }
+      }
+      if (valid) {
+        if (posrow) {
+          const float4* q4 = reinterpret_cast<const float4*>(posrow + n0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b = __ldg(q4 + i);
+            v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+          }
+        }
+        float4* o = reinterpret_cast<float4*>(p.out + static_cast<size_t>(m) * p.ldo + n0);
+        if (p.resid) {
+          const float4* r4 =
+              reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(m) * p.ldo + n0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b = r4[i];
+            v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          o[i] = make_float4(v[4 * i + 0], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue 3: grouped row LayerNorm.  x = acc + bias + resid; per group of `group` consecutive
+// columns: y = (x - mean) / sqrt(var + eps) * gamma[n % group] + beta[n % group]; y = act(y).
+// The tile must hold whole groups (BN % group == 0).  Three TMEM passes (mean, var, write) keep the
+// exact two-pass variance of torch.  Outputs (each optional): fp16 row-major, fp32 row-major,
+// fp32 NCHW ([b, n, tok] with tok = m % tokens, b = m / tokens) for the API-visible embeddings.
+// ------------------------------------------------------------------------------------------------
+struct EpiLN {
+  struct Params {
+    __half* out16;        // [M, ldo] or null
+    float* out32;         // [M, ldo] or null
+    float* out_nchw;      // [M/tokens, N, tokens] or null
+    const float* bias;    // [N] or null
+    const float* resid;   // [M, ldo] fp32 or null
+    const float* gamma;   // [group]
+    const float* beta;    // [group]
+    float eps;
+    int ldo;
+    int group;
+    int act;
+    int tokens;
+    int n_total;
+  };
+  static __device__ __forceinline__ void load_x(const Params& p, int m, bool valid, int n0,
+                                                int chunk, const TmemRow& row, float (&v)[32]) {
+    row.load(chunk, v);
+    if (p.bias) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 b = __ldg(b4 + i);
+        v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+      }
+    }
+    if (p.resid && valid) {
+      const float4* r4 =
+          reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(m) * p.ldo + n0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 b = r4[i];
+        v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+      }
+    }
+  }
+  static __device__ __forceinline__ void run(const Params& p, int m, bool valid, int n_base,
+                                             int n_cols, const TmemRow& row) {
+    const int cpg = p.group >> 5;              // chunks per group
+    const int ngroups = n_cols / p.group;
+    const float inv_g = 1.0f / static_cast<float>(p.group);
+    for (int g = 0; g < ngroups; ++g) {
+      float mean = 0.f;
+      for (int c = 0; c < cpg; ++c) {
+        float v[32];
+        load_x(p, m, valid, n_base + (g * cpg + c) * 32, g * cpg + c, row, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mean += v[i];
+      }
+      mean *= inv_g;
+      float var = 0.f;
+      for (int c = 0; c < cpg; ++c) {
+        float v[32];
+        load_x(p, m, valid, n_base + (g * cpg + c) * 32, g * cpg + c, row, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float d = v[i] - mean;
+          var = fmaf(d, d, var);
+        }
+      }
+      const float rstd = rsqrtf(var * inv_g + p.eps);
+      for (int c = 0; c < cpg; ++c) {
+        float v[32];
+        const int n0 = n_base + (g * cpg + c) * 32;
+        load_x(p, m, valid, n0, g * cpg + c, row, v);
+        const int gi = c * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float y = (v[i] - mean) * rstd * __ldg(p.gamma + gi + i) + __ldg(p.beta + gi + i);
+          v[i] = apply_act(y, p.act);
+        }
+        if (valid) {
+          if (p.out16) {
+            uint4* o = reinterpret_cast<uint4*>(p.out16 + static_cast<size_t>(m) * p.ldo + n0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 u;
+              u.x = pack_half2(v[8 * i + 0], v[8 * i + 1]);
+              u.y = pack_half2(v[8 * i + 2], v[8 * i + 3]);
+              u.z = pack_half2(v[8 * i + 4], v[8 * i + 5]);
+              u.w = pack_half2(v[8 * i + 6], v[8 * i + 7]);
+              o[i] = u;
+            }
+          }
+          if (p.out32) {
+            float4* o = reinterpret_cast<float4*>(p.out32 + static_cast<size_t>(m) * p.ldo + n0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              o[i] = make_float4(v[4 * i + 0], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+          if (p.out_nchw) {
+            const int b = m / p.tokens, t = m % p.tokens;
+            float* o = p.out_nchw + (static_cast<size_t>(b) * p.n_total + n0) * p.tokens + t;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[static_cast<size_t>(i) * p.tokens] = v[i];
+          }
+        }
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue 4: last two stages of the naive map decoder (model.py:292-294,490-491).
+// The GEMM is ConvT(64->32,k2,s2) with columns ordered (sub3, co): a tile row is one 128x128-res
+// ... one stage-3 input pixel; each 32-column chunk is one 2x upsampled sub-pixel with 32 channels.
+// Per chunk: h = GELU(acc + b3) ; ConvT(32->2,k2,s2): out[co, di, dj] = sum_ci h[ci] W4[ci,co,di,dj]
+// + b4[co]; writes logits and sigmoid scores straight into NHWC [B, P, P, 2].
+// Row index r of the GEMM encodes the pixel hierarchy: r = ((b*s*s + i*s + j)*4 + d1)*4 + d2,
+// d = di*2 + dj (see decoder weight packing in pack.cu).
+// ------------------------------------------------------------------------------------------------
+struct EpiDecFinal {
+  struct Params {
+    float* scores;        // [B, P, P, 2] or null
+    float* logits;        // [B, P, P, 2] or null
+    const float* bias3;   // [32]
+    const float* w4;      // [32 ci][8 = (di,dj,co)] fp32
+    const float* bias4;   // [2]
+    int s;                // feature map side (P/16)
+    int P;
+  };
+  static __device__ __forceinline__ void run(const Params& p, int m, bool valid, int n_base,
+                                             int n_cols, const TmemRow& row) {
+    // decode pixel hierarchy of this row
+    const int d2 = m & 3, d1 = (m >> 2) & 3;
+    const int pix = m >> 4;
+    const int ss = p.s * p.s;
+    const int b = pix / ss;
+    const int ij = pix - b * ss;
+    const int i = ij / p.s, j = ij - i * p.s;
+    const int y2 = ((i * 2 + (d1 >> 1)) * 2 + (d2 >> 1));      // row at 4s resolution
+    const int x2 = ((j * 2 + (d1 & 1)) * 2 + (d2 & 1));
+    const float b40 = __ldg(p.bias4 + 0), b41 = __ldg(p.bias4 + 1);
+    for (int c = 0; c < 4; ++c) {                              // c = d3 (n_base == 0, n_cols == 128)
+      float v[32];
+      row.load(c, v);
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = (k & 1) ? b41 : b40;
+#pragma unroll
+      for (int ci = 0; ci < 32; ++ci) {
+        const float h = gelu_erf(v[ci] + __ldg(p.bias3 + ci));
+        const float4 wa = __ldg(reinterpret_cast<const float4*>(p.w4 + ci * 8));
+        const float4 wb = __ldg(reinterpret_cast<const float4*>(p.w4 + ci * 8 + 4));
+        o[0] = fmaf(h, wa.x, o[0]); o[1] = fmaf(h, wa.y, o[1]);
+        o[2] = fmaf(h, wa.z, o[2]); o[3] = fmaf(h, wa.w, o[3]);
+        o[4] = fmaf(h, wb.x, o[4]); o[5] = fmaf(h, wb.y, o[5]);
+        o[6] = fmaf(h, wb.z, o[6]); o[7] = fmaf(h, wb.w, o[7]);
+      }
+      if (valid) {
+        const int y3 = y2 * 2 + (c >> 1), x3 = x2 * 2 + (c & 1);   // 8s resolution
+#pragma unroll
+        for (int di = 0; di < 2; ++di) {
+          const size_t off =
+              ((static_cast<size_t>(b) * p.P + (y3 * 2 + di)) * p.P + x3 * 2) * 2;
+          const float4 lg = make_float4(o[di * 4 + 0], o[di * 4 + 1], o[di * 4 + 2], o[di * 4 + 3]);
+          if (p.logits) *reinterpret_cast<float4*>(p.logits + off) = lg;
+          if (p.scores)
+            *reinterpret_cast<float4*>(p.scores + off) =
+                make_float4(sigmoidf_(lg.x), sigmoidf_(lg.y), sigmoidf_(lg.z), sigmoidf_(lg.w));
+        }
+      }
+    }
+    (void)n_base; (void)n_cols;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// The kernel
+// ------------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int kABytes = kGemmBM * kGemmBK * 2;
+  static constexpr int kBBytes = BN * kGemmBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = STAGES * kStageBytes;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;   // barriers + alignment slack
+};
+
+template <int BN, int STAGES, class Epi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               int M, int N, int K, typename Epi::Params ep) {
+  using SM = GemmSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_m = (M + kGemmBM - 1) / kGemmBM;
+  const int num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = (K + kGemmBK - 1) / kGemmBK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + stage * SM::kStageBytes;
+          uint8_t* sb = sa + SM::kABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], SM::kStageBytes);
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * kGemmBK, m_blk * kGemmBM);
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * kGemmBK, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(kGemmBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[as], aphase ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(smem + stage * SM::kStageBytes);
+          const uint64_t adesc = umma_desc_k128(a_addr);
+          const uint64_t bdesc = umma_desc_k128(a_addr + SM::kABytes);
+#pragma unroll
+          for (int k = 0; k < kGemmBK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in addr>>4 units
+            umma_f16_ss(tmem_d, adesc + static_cast<uint64_t>(2 * k),
+                        bdesc + static_cast<uint64_t>(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&tfull_bar[as]);
+        as ^= 1;
+        if (as == 0) aphase ^= 1u;
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;   // TMEM lane quarter this warp may access
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after_sync();
+      const int m = m_blk * kGemmBM + q * 32 + lane;
+      const int n_base = n_blk * BN;
+      const int n_cols = min(BN, N - n_base);
+      TmemRow row{tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                  static_cast<uint32_t>(as * BN)};
+      Epi::run(ep, m, m < M, n_base, n_cols, row);
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      as ^= 1;
+      if (as == 0) aphase ^= 1u;
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launcher
+// ------------------------------------------------------------------------------------------------
+int device_sm_count();
+
+template <int BN, int STAGES, class Epi>
+int launch_gemm_tc(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K,
+                   const typename Epi::Params& ep, cudaStream_t stream) {
+  using SM = GemmSmem<BN, STAGES>;
+  SRB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  SRB_REQUIRE(N % 32 == 0, "gemm: N=%d must be a multiple of 32", N);
+  SRB_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0,
+              "gemm: K/lda/ldw (%d/%d/%d) must be multiples of 8", K, lda, ldw);
+  CUtensorMap tmA, tmB;
+  if (int rc = make_tmap_f16_2d(&tmA, A, M, K, lda, kGemmBM)) return rc;
+  if (int rc = make_tmap_f16_2d(&tmB, W, N, K, ldw, BN)) return rc;
+  auto kern = gemm_tc_kernel<BN, STAGES, Epi>;
+  static bool attr_set = false;   // per template instantiation
+  if (!attr_set) {
+    SRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
+    attr_set = true;
+  }
+  const int num_tiles = ((M + kGemmBM - 1) / kGemmBM) * ((N + BN - 1) / BN);
+  const int grid = num_tiles < device_sm_count() ? num_tiles : device_sm_count();
+  kern<<<grid, kGemmThreads, SM::kTotal, stream>>>(tmA, tmB, M, N, K, ep);
+  SRB_CUDA_OK(cudaGetLastError());
+  note_launch(1);
+  return 0;
+}
+
+}  // namespace srb

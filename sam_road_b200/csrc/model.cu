@@ -1,0 +1,728 @@
+// sam_road_b200 :: handle, weight packing and the forward orchestration behind the C ABI.
+//
+// Reference call stack reproduced: SAMRoad.infer_masks_and_img_features
+// (model.py:459-495) -> ImageEncoderViT.forward (image_encoder.py:106-116) -> map_decoder
+// (model.py:284-295,490-491); SAMRoad.infer_toponet (model.py:498-508) -> BilinearSampler
+// (model.py:34-58) -> TopoNet.forward (model.py:88-148).
+#include "../../include/samroad_b200.h"
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "ops.h"
+
+using namespace srb;
+
+namespace {
+
+struct HostTensor {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto d : shape) n *= d;
+    return n;
+  }
+};
+
+struct BlockW {
+  float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  __half* qkv_w;  float* qkv_b;
+  __half* proj_w; float* proj_b;
+  float *rel_h, *rel_w;
+  __half* lin1_w; float* lin1_b;
+  __half* lin2_w; float* lin2_b;
+  int win;   // attention window (14) or s for global blocks
+};
+
+struct TopoLayerW {
+  __half* in_w;  float* in_b;
+  __half* out_w; float* out_b;
+  __half* l1_w;  float* l1_b;
+  __half* l2_w;  float* l2_b;
+  float *n1_g, *n1_b, *n2_g, *n2_b;
+};
+
+}  // namespace
+
+struct samroad_ctx {
+  SamRoadCfg cfg;
+  int device = 0;
+  int s = 0, T = 0, D = 0, hd = 0;
+  bool finalized = false;
+  std::map<std::string, HostTensor> staged;
+
+  // device weight arena
+  std::vector<void*> weight_allocs;
+
+  // encoder
+  __half* pe_w = nullptr; float* pe_b = nullptr; float* pos = nullptr;
+  std::vector<BlockW> blocks;
+  __half* neck0_w = nullptr; float *neck1_g = nullptr, *neck1_b = nullptr;
+  __half* neck2_w = nullptr; float *neck3_g = nullptr, *neck3_b = nullptr;
+  // naive decoder
+  __half* dec1_w = nullptr; float* dec1_b = nullptr; float *dec_ln_g = nullptr, *dec_ln_b = nullptr;
+  __half* dec2_w = nullptr; float* dec2_b = nullptr;
+  __half* dec3_w = nullptr; float* dec3_b = nullptr;
+  float* dec4_w = nullptr; float* dec4_b = nullptr;
+  // toponet
+  __half* tp_feat_w = nullptr; float* tp_feat_b = nullptr;
+  __half* tp_st_w = nullptr; float* tp_off_w = nullptr; float* tp_pair_b = nullptr;
+  TopoLayerW tp_layers[3];
+  float* tp_out_w = nullptr; float* tp_out_b = nullptr;
+
+  // activation workspace (grown on demand)
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  // staging for the host-buffer entry point
+  void* stage_in = nullptr;  size_t stage_in_bytes = 0;
+  float* stage_scores = nullptr; size_t stage_scores_bytes = 0;
+  float* stage_emb = nullptr; size_t stage_emb_bytes = 0;
+};
+
+namespace {
+
+constexpr float kPixelMean[3] = {123.675f, 116.28f, 103.53f};   // model.py:229
+constexpr float kPixelStd[3] = {58.395f, 57.12f, 57.375f};      // model.py:230
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- staged-tensor access -----------------------------------------------------------------------
+struct Packer {
+  samroad_ctx* h;
+  bool ok = true;
+  char msg[512] = "";
+
+  const HostTensor* get(const std::string& key, std::initializer_list<int64_t> shape) {
+    auto it = h->staged.find(key);
+    if (it == h->staged.end()) {
+      fail("missing state_dict key '%s'", key.c_str());
+      return nullptr;
+    }
+    const HostTensor& t = it->second;
+    bool same = t.shape.size() == shape.size();
+    if (same) {
+      size_t i = 0;
+      for (auto d : shape) same = same && (t.shape[i++] == d);
+    }
+    if (!same) {
+      std::string got;
+      for (auto d : t.shape) got += std::to_string(d) + ",";
+      std::string want;
+      for (auto d : shape) want += std::to_string(d) + ",";
+      fail("state_dict key '%s' has shape [%s] but [%s] is required", key.c_str(), got.c_str(),
+           want.c_str());
+      return nullptr;
+    }
+    return &t;
+  }
+  void fail(const char* fmt, ...) {
+    if (!ok) return;
+    ok = false;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(msg, sizeof(msg), fmt, ap);
+    va_end(ap);
+  }
+  template <typename T>
+  T* upload(const std::vector<T>& v) {
+    if (!ok) return nullptr;
+    void* d = nullptr;
+    if (cudaMalloc(&d, v.size() * sizeof(T) + 256) != cudaSuccess) {
+      fail("cudaMalloc of %zu bytes for weights failed", v.size() * sizeof(T));
+      return nullptr;
+    }
+    h->weight_allocs.push_back(d);
+    if (cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) {
+      fail("cudaMemcpy of weights failed");
+      return nullptr;
+    }
+    return static_cast<T*>(d);
+  }
+  float* f32(const std::string& key, std::initializer_list<int64_t> shape) {
+    const HostTensor* t = get(key, shape);
+    return t ? upload(t->data) : nullptr;
+  }
+  static std::vector<__half> to_half(const std::vector<float>& v) {
+    std::vector<__half> o(v.size());
+    for (size_t i = 0; i < v.size(); ++i) o[i] = __float2half_rn(v[i]);
+    return o;
+  }
+  // nn.Linear weight [out, in] is already the K-major [N, K] operand
+  __half* linear_w(const std::string& key, int64_t n, int64_t k) {
+    const HostTensor* t = get(key, {n, k});
+    return t ? upload(to_half(t->data)) : nullptr;
+  }
+};
+
+std::string fmt_key(const char* fmt, int i) {
+  char buf[256];
+  snprintf(buf, sizeof(buf), fmt, i);
+  return buf;
+}
+
+bool is_global_block(const SamRoadCfg& c, int i) {
+  for (int k = 0; k < 4; ++k)
+    if (c.global_attn_indexes[k] == i) return true;
+  return false;
+}
+
+// ConvTranspose2d(k=2,s=2) weight [Cin, Cout, 2, 2] -> GEMM operand [N = (d, co), K = ci] with
+// d = di*2 + dj, so that output column block d is sub-pixel (di,dj).
+std::vector<__half> pack_convT(const HostTensor& w, int cin, int cout) {
+  std::vector<__half> o(static_cast<size_t>(4) * cout * cin);
+  for (int ci = 0; ci < cin; ++ci)
+    for (int co = 0; co < cout; ++co)
+      for (int d = 0; d < 4; ++d)
+        o[(static_cast<size_t>(d) * cout + co) * cin + ci] =
+            __float2half_rn(w.data[(static_cast<size_t>(ci) * cout + co) * 4 + d]);
+  return o;
+}
+std::vector<float> tile4(const std::vector<float>& b) {
+  std::vector<float> o(b.size() * 4);
+  for (int d = 0; d < 4; ++d)
+    for (size_t i = 0; i < b.size(); ++i) o[d * b.size() + i] = b[i];
+  return o;
+}
+
+int ensure_bytes(void** p, size_t* cur, size_t need) {
+  if (*cur >= need) return 0;
+  if (*p) {
+    SRB_CUDA_OK(cudaDeviceSynchronize());
+    SRB_CUDA_OK(cudaFree(*p));
+    *p = nullptr;
+    *cur = 0;
+  }
+  SRB_CUDA_OK(cudaMalloc(p, need));
+  *cur = need;
+  return 0;
+}
+
+// ---- activation workspace layout for the encoder + decoder ------------------------------------------
+struct EncWs {
+  float* X;        // [M, D]   residual stream (fp32)
+  __half* XN;      // [M, max(D,768)] LN output / patch im2col / fp16 copy of X
+  __half* QKV;     // [M, 3D]
+  __half* ATT;     // [M, D]
+  __half* H;       // [M, 4D]  MLP hidden; reused: IM2 [M, 2304], D2 [4M, 256]
+  __half* N1;      // [M, 256] neck conv1 + LN ; reused: D1 [M, 512] needs 2x -> own buffer below
+  __half* FEAT;    // [M, 256] neck output (fp16 NHWC)
+  __half* D1;      // [M, 512]
+  size_t total;
+};
+
+EncWs layout_enc(const samroad_ctx* h, int B, void* base) {
+  const size_t M = static_cast<size_t>(B) * h->T, D = h->D;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += align_up(bytes, 1024);
+    return o;
+  };
+  EncWs w;
+  char* b = static_cast<char*>(base);
+  w.X = reinterpret_cast<float*>(b + take(M * D * 4));
+  w.XN = reinterpret_cast<__half*>(b + take(M * (D > 768 ? D : 768) * 2));
+  w.QKV = reinterpret_cast<__half*>(b + take(M * 3 * D * 2));
+  w.ATT = reinterpret_cast<__half*>(b + take(M * D * 2));
+  const size_t hbytes = M * 4 * D * 2;   // >= M*2304*2 and >= 4M*256*2 for D >= 768
+  w.H = reinterpret_cast<__half*>(b + take(hbytes));
+  w.N1 = reinterpret_cast<__half*>(b + take(M * 256 * 2));
+  w.FEAT = reinterpret_cast<__half*>(b + take(M * 256 * 2));
+  w.D1 = reinterpret_cast<__half*>(b + take(M * 512 * 2));
+  w.total = off;
+  return w;
+}
+
+struct TopoWs {
+  __half* F16;     // [B*N, 256]
+  __half* PF16;    // [B*N, 128]
+  float* PST;      // [B*N, 256]
+  uint8_t* VF;     // [rows*Np]
+  float* X32;      // [tok, 128]
+  __half* X16;     // [tok, 128]
+  __half* QKV16;   // [tok, 384]
+  __half* ATT16;   // [tok, 128]
+  __half* H16;     // [tok, 128]
+  size_t total;
+};
+
+TopoWs layout_topo(int B, int N, int Ns, int Np, void* base) {
+  const size_t pts = static_cast<size_t>(B) * N, tok = static_cast<size_t>(B) * Ns * Np;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += align_up(bytes, 1024);
+    return o;
+  };
+  TopoWs w;
+  char* b = static_cast<char*>(base);
+  w.F16 = reinterpret_cast<__half*>(b + take(pts * 256 * 2));
+  w.PF16 = reinterpret_cast<__half*>(b + take(pts * 128 * 2));
+  w.PST = reinterpret_cast<float*>(b + take(pts * 256 * 4));
+  w.VF = reinterpret_cast<uint8_t*>(b + take(tok));
+  w.X32 = reinterpret_cast<float*>(b + take(tok * 128 * 4));
+  w.X16 = reinterpret_cast<__half*>(b + take(tok * 128 * 2));
+  w.QKV16 = reinterpret_cast<__half*>(b + take(tok * 384 * 2));
+  w.ATT16 = reinterpret_cast<__half*>(b + take(tok * 128 * 2));
+  w.H16 = reinterpret_cast<__half*>(b + take(tok * 128 * 2));
+  w.total = off;
+  return w;
+}
+
+#define SRB_TRY(expr)            \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != 0) return _rc;    \
+  } while (0)
+
+int check_handle(samroad_handle_t h, bool need_weights) {
+  SRB_REQUIRE(h != nullptr, "null samroad handle");
+  SRB_REQUIRE(!need_weights || h->finalized,
+              "weights not finalized: call samroad_load_tensor for every state_dict key, then "
+              "samroad_finalize_weights");
+  SRB_CUDA_OK(cudaSetDevice(h->device));
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+// lifetime
+// =================================================================================================
+extern "C" int samroad_create(const SamRoadCfg* cfg, int device, samroad_handle_t* out) {
+  SRB_REQUIRE(cfg && out, "samroad_create: null argument");
+  SRB_REQUIRE(cfg->patch_size > 0 && cfg->patch_size % 16 == 0 && cfg->patch_size <= 1024,
+              "PATCH_SIZE=%d must be a multiple of 16 in (0,1024]", cfg->patch_size);
+  SRB_REQUIRE(cfg->embed_dim % 128 == 0 && cfg->embed_dim >= 768 && cfg->embed_dim <= 1280,
+              "embed_dim=%d unsupported", cfg->embed_dim);
+  SRB_REQUIRE(cfg->num_heads > 0 && cfg->embed_dim % cfg->num_heads == 0,
+              "embed_dim=%d not divisible by num_heads=%d", cfg->embed_dim, cfg->num_heads);
+  const int hd = cfg->embed_dim / cfg->num_heads;
+  SRB_REQUIRE(hd == 64 || hd == 80, "head_dim=%d unsupported (64 or 80)", hd);
+  SRB_REQUIRE(cfg->depth > 0 && cfg->depth <= 64, "depth=%d unsupported", cfg->depth);
+  SRB_REQUIRE(cfg->window_size > 0, "window_size=%d must be positive", cfg->window_size);
+  SRB_REQUIRE(cfg->use_sam_decoder == 0,
+              "USE_SAM_DECODER=True (SAM TwoWayTransformer mask decoder) is not built yet in this "
+              "library; only the default naive map_decoder path (model.py:284-295) is available");
+  int ndev = 0;
+  SRB_CUDA_OK(cudaGetDeviceCount(&ndev));
+  SRB_REQUIRE(ndev > 0, "no CUDA device: libsamroad_b200 has no CPU fallback");
+  SRB_REQUIRE(device >= 0 && device < ndev, "device %d out of range (0..%d)", device, ndev - 1);
+  SRB_CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  SRB_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  SRB_REQUIRE(prop.major == 10, "device %d is sm_%d%d; this library is built for sm_100a only",
+              device, prop.major, prop.minor);
+  samroad_ctx* h = new samroad_ctx();
+  h->cfg = *cfg;
+  h->device = device;
+  h->s = cfg->patch_size / 16;
+  h->T = h->s * h->s;
+  h->D = cfg->embed_dim;
+  h->hd = hd;
+  *out = h;
+  return 0;
+}
+
+extern "C" int samroad_destroy(samroad_handle_t h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (void* p : h->weight_allocs) cudaFree(p);
+  if (h->ws) cudaFree(h->ws);
+  if (h->stage_in) cudaFree(h->stage_in);
+  if (h->stage_scores) cudaFree(h->stage_scores);
+  if (h->stage_emb) cudaFree(h->stage_emb);
+  delete h;
+  return 0;
+}
+
+extern "C" int samroad_load_tensor(samroad_handle_t h, const char* key, const float* host_data,
+                                   const int64_t* shape, int ndim) {
+  SRB_REQUIRE(h && key && host_data && (shape || ndim == 0), "samroad_load_tensor: null argument");
+  SRB_REQUIRE(ndim >= 0 && ndim <= 8, "samroad_load_tensor: ndim=%d", ndim);
+  HostTensor t;
+  t.shape.assign(shape, shape + ndim);
+  const int64_t n = t.numel();
+  SRB_REQUIRE(n >= 0, "samroad_load_tensor: negative size for '%s'", key);
+  t.data.assign(host_data, host_data + n);
+  h->staged[key] = std::move(t);
+  h->finalized = false;
+  return 0;
+}
+
+extern "C" int samroad_finalize_weights(samroad_handle_t h) {
+  SRB_TRY(check_handle(h, false));
+  // drop previously packed weights (re-load after load_state_dict)
+  SRB_CUDA_OK(cudaDeviceSynchronize());
+  for (void* p : h->weight_allocs) cudaFree(p);
+  h->weight_allocs.clear();
+  h->blocks.clear();
+
+  Packer P{h};
+  const SamRoadCfg& c = h->cfg;
+  const int64_t D = h->D, s = h->s, hd = h->hd;
+
+  // ---- patch embed: [D,3,16,16] -> [D, 768] with k = ky*48 + kx*3 + c (matches im2col_patch16) ----
+  if (const HostTensor* w = P.get("image_encoder.patch_embed.proj.weight", {D, 3, 16, 16})) {
+    std::vector<__half> o(static_cast<size_t>(D) * 768);
+    for (int64_t n = 0; n < D; ++n)
+      for (int ch = 0; ch < 3; ++ch)
+        for (int ky = 0; ky < 16; ++ky)
+          for (int kx = 0; kx < 16; ++kx)
+            o[n * 768 + ky * 48 + kx * 3 + ch] =
+                __float2half_rn(w->data[((n * 3 + ch) * 16 + ky) * 16 + kx]);
+    h->pe_w = P.upload(o);
+  }
+  h->pe_b = P.f32("image_encoder.patch_embed.proj.bias", {D});
+  h->pos = P.f32("image_encoder.pos_embed", {1, s, s, D});
+
+  // ---- transformer blocks ----
+  h->blocks.resize(c.depth);
+  for (int i = 0; i < c.depth && P.ok; ++i) {
+    BlockW& b = h->blocks[i];
+    const bool glob = is_global_block(c, i);
+    b.win = glob ? static_cast<int>(s) : (c.window_size < s ? c.window_size : static_cast<int>(s));
+    // window blocks keep their 14x14 rel-pos tables even when s < 14 is never the case here
+    const int64_t rel_rows = glob ? 2 * s - 1 : 2 * c.window_size - 1;
+    auto K = [&](const char* suffix) { return fmt_key("image_encoder.blocks.%d.", i) + suffix; };
+    b.ln1_g = P.f32(K("norm1.weight"), {D});
+    b.ln1_b = P.f32(K("norm1.bias"), {D});
+    b.ln2_g = P.f32(K("norm2.weight"), {D});
+    b.ln2_b = P.f32(K("norm2.bias"), {D});
+    // qkv (+ LoRA merge: qkv = xW^T + b ; q += B_q A_q x ; v += B_v A_v x   model.py:179-186)
+    if (const HostTensor* w = P.get(K("attn.qkv.weight"), {3 * D, D})) {
+      std::vector<float> wf = w->data;
+      if (c.lora_rank > 0) {
+        const int64_t r = c.lora_rank;
+        const HostTensor* aq = P.get(K("attn.qkv.linear_a_q.weight"), {r, D});
+        const HostTensor* bq = P.get(K("attn.qkv.linear_b_q.weight"), {D, r});
+        const HostTensor* av = P.get(K("attn.qkv.linear_a_v.weight"), {r, D});
+        const HostTensor* bv = P.get(K("attn.qkv.linear_b_v.weight"), {D, r});
+        if (aq && bq && av && bv) {
+          for (int64_t n = 0; n < D; ++n)
+            for (int64_t j = 0; j < r; ++j) {
+              const float bqv = bq->data[n * r + j], bvv = bv->data[n * r + j];
+              float* wq = &wf[n * D];
+              float* wv = &wf[(2 * D + n) * D];
+              const float* aqr = &aq->data[j * D];
+              const float* avr = &av->data[j * D];
+              for (int64_t k = 0; k < D; ++k) {
+                wq[k] += bqv * aqr[k];
+                wv[k] += bvv * avr[k];
+              }
+            }
+        }
+      }
+      b.qkv_w = P.upload(Packer::to_half(wf));
+    }
+    b.qkv_b = P.f32(K("attn.qkv.bias"), {3 * D});
+    b.proj_w = P.linear_w(K("attn.proj.weight"), D, D);
+    b.proj_b = P.f32(K("attn.proj.bias"), {D});
+    b.rel_h = P.f32(K("attn.rel_pos_h"), {rel_rows, hd});
+    b.rel_w = P.f32(K("attn.rel_pos_w"), {rel_rows, hd});
+    b.lin1_w = P.linear_w(K("mlp.lin1.weight"), 4 * D, D);
+    b.lin1_b = P.f32(K("mlp.lin1.bias"), {4 * D});
+    b.lin2_w = P.linear_w(K("mlp.lin2.weight"), D, 4 * D);
+    b.lin2_b = P.f32(K("mlp.lin2.bias"), {D});
+    if (!glob && c.window_size > s)
+      P.fail("window_size=%d larger than the %lld-token feature map is not supported",
+             c.window_size, (long long)s);
+  }
+
+  // ---- neck (image_encoder.py:88-104) ----
+  if (const HostTensor* w = P.get("image_encoder.neck.0.weight", {256, D, 1, 1}))
+    h->neck0_w = P.upload(Packer::to_half(w->data));
+  h->neck1_g = P.f32("image_encoder.neck.1.weight", {256});
+  h->neck1_b = P.f32("image_encoder.neck.1.bias", {256});
+  if (const HostTensor* w = P.get("image_encoder.neck.2.weight", {256, 256, 3, 3})) {
+    std::vector<__half> o(static_cast<size_t>(256) * 2304);   // [n][tap*256 + c]
+    for (int n = 0; n < 256; ++n)
+      for (int ch = 0; ch < 256; ++ch)
+        for (int tap = 0; tap < 9; ++tap)
+          o[static_cast<size_t>(n) * 2304 + tap * 256 + ch] =
+              __float2half_rn(w->data[(static_cast<size_t>(n) * 256 + ch) * 9 + tap]);
+    h->neck2_w = P.upload(o);
+  }
+  h->neck3_g = P.f32("image_encoder.neck.3.weight", {256});
+  h->neck3_b = P.f32("image_encoder.neck.3.bias", {256});
+
+  // ---- naive map decoder (model.py:286-295) ----
+  if (const HostTensor* w = P.get("map_decoder.0.weight", {256, 128, 2, 2}))
+    h->dec1_w = P.upload(pack_convT(*w, 256, 128));
+  if (const HostTensor* b = P.get("map_decoder.0.bias", {128})) h->dec1_b = P.upload(tile4(b->data));
+  h->dec_ln_g = P.f32("map_decoder.1.weight", {128});
+  h->dec_ln_b = P.f32("map_decoder.1.bias", {128});
+  if (const HostTensor* w = P.get("map_decoder.3.weight", {128, 64, 2, 2}))
+    h->dec2_w = P.upload(pack_convT(*w, 128, 64));
+  if (const HostTensor* b = P.get("map_decoder.3.bias", {64})) h->dec2_b = P.upload(tile4(b->data));
+  if (const HostTensor* w = P.get("map_decoder.5.weight", {64, 32, 2, 2}))
+    h->dec3_w = P.upload(pack_convT(*w, 64, 32));
+  h->dec3_b = P.f32("map_decoder.5.bias", {32});
+  if (const HostTensor* w = P.get("map_decoder.7.weight", {32, 2, 2, 2})) {
+    std::vector<float> o(32 * 8);   // [ci][di*4 + dj*2 + co]
+    for (int ci = 0; ci < 32; ++ci)
+      for (int co = 0; co < 2; ++co)
+        for (int d = 0; d < 4; ++d) o[ci * 8 + d * 2 + co] = w->data[(ci * 2 + co) * 4 + d];
+    h->dec4_w = P.upload(o);
+  }
+  h->dec4_b = P.f32("map_decoder.7.bias", {2});
+
+  // ---- TopoNet (model.py:61-86) ----
+  h->tp_feat_w = P.linear_w("topo_net.feature_proj.weight", 128, 256);
+  h->tp_feat_b = P.f32("topo_net.feature_proj.bias", {128});
+  if (const HostTensor* w = P.get("topo_net.pair_proj.weight", {128, 258})) {
+    std::vector<__half> st(static_cast<size_t>(256) * 128);   // rows 0..127: Ws, 128..255: Wt
+    std::vector<float> off(128 * 2);
+    for (int n = 0; n < 128; ++n) {
+      for (int k = 0; k < 128; ++k) {
+        st[static_cast<size_t>(n) * 128 + k] = __float2half_rn(w->data[n * 258 + k]);
+        st[static_cast<size_t>(128 + n) * 128 + k] = __float2half_rn(w->data[n * 258 + 128 + k]);
+      }
+      off[n * 2 + 0] = w->data[n * 258 + 256];
+      off[n * 2 + 1] = w->data[n * 258 + 257];
+    }
+    h->tp_st_w = P.upload(st);
+    h->tp_off_w = P.upload(off);
+  }
+  h->tp_pair_b = P.f32("topo_net.pair_proj.bias", {128});
+  if (c.toponet_version != SAMROAD_TOPO_NO_TRANSFORMER) {
+    for (int l = 0; l < 3; ++l) {
+      TopoLayerW& t = h->tp_layers[l];
+      auto K = [&](const char* suffix) {
+        return fmt_key("topo_net.transformer_encoder.layers.%d.", l) + suffix;
+      };
+      t.in_w = P.linear_w(K("self_attn.in_proj_weight"), 384, 128);
+      t.in_b = P.f32(K("self_attn.in_proj_bias"), {384});
+      t.out_w = P.linear_w(K("self_attn.out_proj.weight"), 128, 128);
+      t.out_b = P.f32(K("self_attn.out_proj.bias"), {128});
+      t.l1_w = P.linear_w(K("linear1.weight"), 128, 128);
+      t.l1_b = P.f32(K("linear1.bias"), {128});
+      t.l2_w = P.linear_w(K("linear2.weight"), 128, 128);
+      t.l2_b = P.f32(K("linear2.bias"), {128});
+      t.n1_g = P.f32(K("norm1.weight"), {128});
+      t.n1_b = P.f32(K("norm1.bias"), {128});
+      t.n2_g = P.f32(K("norm2.weight"), {128});
+      t.n2_b = P.f32(K("norm2.bias"), {128});
+    }
+  }
+  h->tp_out_w = P.f32("topo_net.output_proj.weight", {1, 128});
+  h->tp_out_b = P.f32("topo_net.output_proj.bias", {1});
+
+  if (!P.ok) {
+    set_last_error("samroad_finalize_weights: %s", P.msg);
+    return 3;
+  }
+  h->staged.clear();
+  h->finalized = true;
+  return 0;
+}
+
+// =================================================================================================
+// encoder + mask head
+// =================================================================================================
+extern "C" size_t samroad_workspace_bytes(samroad_handle_t h, int B) {
+  if (!h || B <= 0) return 0;
+  return layout_enc(h, B, nullptr).total;
+}
+
+extern "C" int samroad_encode_masks(samroad_handle_t h, const void* rgb, int rgb_dtype, int B,
+                                    float* mask_scores, float* mask_logits,
+                                    float* image_embeddings, void* stream) {
+  SRB_TRY(check_handle(h, true));
+  SRB_REQUIRE(rgb && image_embeddings, "samroad_encode_masks: null rgb / image_embeddings");
+  SRB_REQUIRE(rgb_dtype == SAMROAD_F32 || rgb_dtype == SAMROAD_U8,
+              "samroad_encode_masks: rgb dtype %d (want SAMROAD_F32 or SAMROAD_U8)", rgb_dtype);
+  if (B <= 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int T = h->T, D = h->D, s = h->s, P = h->cfg.patch_size;
+  const long Ml = static_cast<long>(B) * T;
+  SRB_REQUIRE(Ml * 16 < 2147483647L, "batch of %d tiles is too large for one call", B);
+  const int M = static_cast<int>(Ml);
+  SRB_TRY(ensure_bytes(&h->ws, &h->ws_bytes, layout_enc(h, B, nullptr).total));
+  EncWs w = layout_enc(h, B, h->ws);
+
+  // patch embed + pos embed  (image_encoder.py:107-109, 387-395; normalisation model.py:465-467)
+  const float inv_std[3] = {1.0f / kPixelStd[0], 1.0f / kPixelStd[1], 1.0f / kPixelStd[2]};
+  SRB_TRY(im2col_patch16(rgb, rgb_dtype == SAMROAD_U8 ? 1 : 0, B, P, kPixelMean, inv_std, w.XN, st));
+  SRB_TRY(gemm_f32out(w.XN, 768, h->pe_w, 768, M, D, 768, h->pe_b, nullptr, h->pos, T, w.X, D, st));
+
+  // transformer blocks (image_encoder.py:166-182)
+  for (int i = 0; i < h->cfg.depth; ++i) {
+    const BlockW& b = h->blocks[i];
+    SRB_TRY(layernorm_f16(w.X, b.ln1_g, b.ln1_b, 1e-6f, M, D, w.XN, st));
+    SRB_TRY(gemm_f16out(w.XN, D, b.qkv_w, D, M, 3 * D, D, b.qkv_b, ACT_NONE, w.QKV, 3 * D, st));
+    SRB_TRY(encoder_attention(w.QKV, b.qkv_b, b.rel_h, b.rel_w, B, s, b.win, h->cfg.num_heads,
+                              h->hd, w.ATT, st));
+    SRB_TRY(gemm_f32out(w.ATT, D, b.proj_w, D, M, D, D, b.proj_b, w.X, nullptr, 0, w.X, D, st));
+    SRB_TRY(layernorm_f16(w.X, b.ln2_g, b.ln2_b, 1e-6f, M, D, w.XN, st));
+    SRB_TRY(gemm_f16out(w.XN, D, b.lin1_w, D, M, 4 * D, D, b.lin1_b, ACT_GELU, w.H, 4 * D, st));
+    SRB_TRY(gemm_f32out(w.H, 4 * D, b.lin2_w, 4 * D, M, D, 4 * D, b.lin2_b, w.X, nullptr, 0, w.X, D,
+                        st));
+  }
+
+  // neck (image_encoder.py:88-104,114): 1x1 conv -> LN2d -> 3x3 conv -> LN2d
+  SRB_TRY(convert_f32_f16(w.X, static_cast<long>(M) * D, w.XN, st));
+  SRB_TRY(gemm_ln(w.XN, D, h->neck0_w, D, M, 256, D, nullptr, nullptr, h->neck1_g, h->neck1_b,
+                  1e-6f, 256, ACT_NONE, w.N1, nullptr, nullptr, T, 256, st));
+  __half* IM2 = w.H;
+  SRB_TRY(im2col_3x3(w.N1, B, s, 256, IM2, st));
+  SRB_TRY(gemm_ln(IM2, 2304, h->neck2_w, 2304, M, 256, 2304, nullptr, nullptr, h->neck3_g,
+                  h->neck3_b, 1e-6f, 256, ACT_NONE, w.FEAT, nullptr, image_embeddings, T, 256, st));
+
+  // naive map decoder (model.py:286-295, 490-491) as three GEMMs, pixel shuffle by row indexing
+  if (mask_scores || mask_logits) {
+    SRB_TRY(gemm_ln(w.FEAT, 256, h->dec1_w, 256, M, 512, 256, h->dec1_b, nullptr, h->dec_ln_g,
+                    h->dec_ln_b, 1e-6f, 128, ACT_GELU, w.D1, nullptr, nullptr, T, 512, st));
+    __half* D2 = w.H;
+    SRB_TRY(gemm_f16out(w.D1, 128, h->dec2_w, 128, 4 * M, 256, 128, h->dec2_b, ACT_GELU, D2, 256,
+                        st));
+    SRB_TRY(gemm_dec_final(D2, 64, h->dec3_w, 64, 16 * M, 64, h->dec3_b, h->dec4_w, h->dec4_b, s, P,
+                           mask_scores, mask_logits, st));
+  }
+  return 0;
+}
+
+extern "C" int samroad_encode_masks_host(samroad_handle_t h, const void* rgb_host, int rgb_dtype,
+                                         int B, float* mask_scores_host,
+                                         float* image_embeddings_host) {
+  SRB_TRY(check_handle(h, true));
+  SRB_REQUIRE(rgb_host, "samroad_encode_masks_host: null rgb");
+  if (B <= 0) return 0;
+  const size_t P = h->cfg.patch_size, s = h->s;
+  const size_t in_bytes = static_cast<size_t>(B) * P * P * 3 * (rgb_dtype == SAMROAD_U8 ? 1 : 4);
+  const size_t sc_bytes = static_cast<size_t>(B) * P * P * 2 * 4;
+  const size_t em_bytes = static_cast<size_t>(B) * 256 * s * s * 4;
+  SRB_TRY(ensure_bytes(&h->stage_in, &h->stage_in_bytes, in_bytes));
+  SRB_TRY(ensure_bytes(reinterpret_cast<void**>(&h->stage_scores), &h->stage_scores_bytes, sc_bytes));
+  SRB_TRY(ensure_bytes(reinterpret_cast<void**>(&h->stage_emb), &h->stage_emb_bytes, em_bytes));
+  cudaStream_t st = nullptr;
+  SRB_CUDA_OK(cudaMemcpyAsync(h->stage_in, rgb_host, in_bytes, cudaMemcpyHostToDevice, st));
+  SRB_TRY(samroad_encode_masks(h, h->stage_in, rgb_dtype, B,
+                               mask_scores_host ? h->stage_scores : nullptr, nullptr, h->stage_emb,
+                               st));
+  if (mask_scores_host)
+    SRB_CUDA_OK(cudaMemcpyAsync(mask_scores_host, h->stage_scores, sc_bytes, cudaMemcpyDeviceToHost,
+                                st));
+  if (image_embeddings_host)
+    SRB_CUDA_OK(cudaMemcpyAsync(image_embeddings_host, h->stage_emb, em_bytes,
+                                cudaMemcpyDeviceToHost, st));
+  SRB_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// =================================================================================================
+// TopoNet
+// =================================================================================================
+extern "C" int samroad_toponet(samroad_handle_t h, const float* image_embeddings,
+                               const void* points, int pts_dtype, const void* pairs,
+                               int pairs_dtype, const uint8_t* valid, int B, int N, int Ns, int Np,
+                               float* topo_logits, float* topo_scores, void* stream) {
+  SRB_TRY(check_handle(h, true));
+  SRB_REQUIRE(image_embeddings && points && pairs && valid, "samroad_toponet: null input");
+  SRB_REQUIRE(pts_dtype == SAMROAD_F32 || pts_dtype == SAMROAD_I64 || pts_dtype == SAMROAD_I32,
+              "samroad_toponet: points dtype %d", pts_dtype);
+  SRB_REQUIRE(pairs_dtype == SAMROAD_I64 || pairs_dtype == SAMROAD_I32,
+              "samroad_toponet: pairs dtype %d", pairs_dtype);
+  SRB_REQUIRE(Np >= 1 && Np <= 16, "samroad_toponet: n_pairs=%d must be in 1..16", Np);
+  if (B <= 0 || Ns <= 0) return 0;
+  SRB_REQUIRE(N > 0, "samroad_toponet: N=%d points but Ns=%d samples", N, Ns);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long tokl = static_cast<long>(B) * Ns * Np;
+  SRB_REQUIRE(tokl < 2147483647L / 4, "samroad_toponet: %ld pair tokens is too many for one call",
+              tokl);
+  const int tok = static_cast<int>(tokl), pts = B * N, rows = B * Ns;
+  // TopoNet shares the activation workspace with the encoder (calls are stream-ordered)
+  SRB_TRY(ensure_bytes(&h->ws, &h->ws_bytes, layout_topo(B, N, Ns, Np, nullptr).total));
+  TopoWs w = layout_topo(B, N, Ns, Np, h->ws);
+  const int zero_off = h->cfg.toponet_version == SAMROAD_TOPO_NO_OFFSET;
+  const bool no_tf = h->cfg.toponet_version == SAMROAD_TOPO_NO_TRANSFORMER;
+
+  SRB_TRY(topo_sample_features(image_embeddings, B, 256, h->s, h->cfg.patch_size, points, pts_dtype,
+                               N, w.F16, st));
+  SRB_TRY(gemm_f16out(w.F16, 256, h->tp_feat_w, 256, pts, 128, 256, h->tp_feat_b, ACT_RELU, w.PF16,
+                      128, st));
+  SRB_TRY(gemm_f32out(w.PF16, 128, h->tp_st_w, 128, pts, 256, 128, nullptr, nullptr, nullptr, 0,
+                      w.PST, 256, st));
+  SRB_TRY(topo_fix_valid(valid, rows, Np, w.VF, st));
+  SRB_TRY(topo_pair_features(w.PST, h->tp_off_w, h->tp_pair_b, points, pts_dtype, pairs,
+                             pairs_dtype, B, N, Ns, Np, zero_off, w.X32, w.X16, st));
+  if (!no_tf) {
+    for (int l = 0; l < 3; ++l) {
+      const TopoLayerW& t = h->tp_layers[l];
+      SRB_TRY(gemm_f16out(w.X16, 128, t.in_w, 128, tok, 384, 128, t.in_b, ACT_NONE, w.QKV16, 384,
+                          st));
+      SRB_TRY(topo_attention(w.QKV16, w.VF, rows, Np, w.ATT16, st));
+      SRB_TRY(gemm_ln(w.ATT16, 128, t.out_w, 128, tok, 128, 128, t.out_b, w.X32, t.n1_g, t.n1_b,
+                      1e-5f, 128, ACT_NONE, w.X16, w.X32, nullptr, 1, 128, st));
+      SRB_TRY(gemm_f16out(w.X16, 128, t.l1_w, 128, tok, 128, 128, t.l1_b, ACT_RELU, w.H16, 128, st));
+      SRB_TRY(gemm_ln(w.H16, 128, t.l2_w, 128, tok, 128, 128, t.l2_b, w.X32, t.n2_g, t.n2_b, 1e-5f,
+                      128, ACT_NONE, w.X16, w.X32, nullptr, 1, 128, st));
+    }
+  }
+  SRB_TRY(topo_output(w.X32, no_tf ? nullptr : w.VF, h->tp_out_w, h->tp_out_b, tok, topo_logits,
+                      topo_scores, st));
+  return 0;
+}
+
+// =================================================================================================
+// misc C ABI
+// =================================================================================================
+extern "C" int samroad_fuse_masks(const float* scores, int n_tiles, int P, const int32_t* tile_x0,
+                                  const int32_t* tile_y0, int H, int W, uint8_t* keypoint_u8,
+                                  uint8_t* road_u8, void* stream) {
+  SRB_REQUIRE(scores && tile_x0 && tile_y0 && keypoint_u8 && road_u8, "samroad_fuse_masks: null");
+  return fuse_masks(scores, n_tiles, P, tile_x0, tile_y0, H, W, keypoint_u8, road_u8,
+                    static_cast<cudaStream_t>(stream));
+}
+
+extern "C" uint64_t samroad_launch_count(int reset) { return launch_count(reset != 0); }
+extern "C" const char* samroad_last_error(void) { return get_last_error(); }
+extern "C" int samroad_abi_version(void) { return SAMROAD_ABI_VERSION; }
+
+extern "C" int samroad_op_gemm_f16(const void* A, int lda, const void* W, int ldw, int M, int N,
+                                   int K, const float* bias, int act, void* out16, int ldo,
+                                   void* stream) {
+  return gemm_f16out(static_cast<const __half*>(A), lda, static_cast<const __half*>(W), ldw, M, N, K,
+                     bias, act, static_cast<__half*>(out16), ldo, static_cast<cudaStream_t>(stream));
+}
+extern "C" int samroad_op_gemm_f32(const void* A, int lda, const void* W, int ldw, int M, int N,
+                                   int K, const float* bias, const float* resid, const float* pos,
+                                   int pos_rows, float* out32, int ldo, void* stream) {
+  return gemm_f32out(static_cast<const __half*>(A), lda, static_cast<const __half*>(W), ldw, M, N, K,
+                     bias, resid, pos, pos_rows, out32, ldo, static_cast<cudaStream_t>(stream));
+}
+extern "C" int samroad_op_gemm_ln(const void* A, int lda, const void* W, int ldw, int M, int N,
+                                  int K, const float* bias, const float* resid, const float* gamma,
+                                  const float* beta, float eps, int group, int act, void* out16,
+                                  float* out32, float* out_nchw, int tokens, int ldo, void* stream) {
+  return gemm_ln(static_cast<const __half*>(A), lda, static_cast<const __half*>(W), ldw, M, N, K,
+                 bias, resid, gamma, beta, eps, group, act, static_cast<__half*>(out16), out32,
+                 out_nchw, tokens, ldo, static_cast<cudaStream_t>(stream));
+}
+extern "C" int samroad_op_gemm_ref(const void* A, int lda, const void* W, int ldw, int M, int N,
+                                   int K, float* out32, int ldo, void* stream) {
+  return gemm_ref_simt(static_cast<const __half*>(A), lda, static_cast<const __half*>(W), ldw, M, N,
+                       K, out32, ldo, static_cast<cudaStream_t>(stream));
+}
+extern "C" int samroad_op_layernorm(const float* x, const float* gamma, const float* beta,
+                                    float eps, int M, int D, void* out16, void* stream) {
+  return layernorm_f16(x, gamma, beta, eps, M, D, static_cast<__half*>(out16),
+                       static_cast<cudaStream_t>(stream));
+}
+extern "C" int samroad_op_attention(const void* qkv16, const float* qkv_bias, const float* rel_h,
+                                    const float* rel_w, int B, int s, int win, int heads,
+                                    int head_dim, void* out16, void* stream) {
+  return encoder_attention(static_cast<const __half*>(qkv16), qkv_bias, rel_h, rel_w, B, s, win,
+                           heads, head_dim, static_cast<__half*>(out16),
+                           static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,71 @@
+// sam_road_b200 :: internal C++ launcher declarations (host side).  Every launcher is stream-ordered,
+// asynchronous, returns 0 on success and sets srb::set_last_error() otherwise.
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace srb {
+
+enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_SIGMOID = 3 };
+
+void set_last_error(const char* fmt, ...);
+const char* get_last_error();
+int device_sm_count();
+void note_launch(int n = 1);
+uint64_t launch_count(bool reset);
+
+// ---- GEMM family (gemm_ops.cu) : C = A[M,K] * W[N,K]^T with fused epilogues ------------------------
+int gemm_f16out(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K,
+                const float* bias, int act, __half* out, int ldo, cudaStream_t st);
+int gemm_f32out(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K,
+                const float* bias, const float* resid, const float* pos, int pos_rows, float* out,
+                int ldo, cudaStream_t st);
+int gemm_ln(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K,
+            const float* bias, const float* resid, const float* gamma, const float* beta, float eps,
+            int group, int act, __half* out16, float* out32, float* out_nchw, int tokens, int ldo,
+            cudaStream_t st);
+int gemm_dec_final(const __half* A, int lda, const __half* W, int ldw, int M, int K,
+                   const float* bias3, const float* w4, const float* bias4, int s, int P,
+                   float* scores, float* logits, cudaStream_t st);
+// plain SIMT fp32-accumulate GEMM used only by the on-device unit tests as an independent checker
+int gemm_ref_simt(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K,
+                  float* out, int ldo, cudaStream_t st);
+
+// ---- elementwise / data-movement kernels (kernels.cu) ------------------------------------------------
+int layernorm_f16(const float* x, const float* gamma, const float* beta, float eps, int M, int D,
+                  __half* out, cudaStream_t st);
+// rgb: [B,P,P,3] fp32 (dtype 0) or uint8 (dtype 1); out: [B*(P/16)^2, 768] fp16, k = ky*48+kx*3+c
+int im2col_patch16(const void* rgb, int dtype, int B, int P, const float* mean, const float* inv_std,
+                   __half* out, cudaStream_t st);
+// x: [B*s*s, C] fp16 NHWC; out: [B*s*s, 9*C], k = (ky*3+kx)*C + c, zero padding 1
+int im2col_3x3(const __half* x, int B, int s, int C, __half* out, cudaStream_t st);
+int convert_f32_f16(const float* x, long n, __half* out, cudaStream_t st);
+
+// ---- encoder attention (attention.cu) --------------------------------------------------------------------
+// qkv: [B*s*s, 3*D] fp16, columns (q|k|v) x head x hd ; out: [B*s*s, D] fp16.
+// win == s means global attention; otherwise window attention over zero-padded LN output, whose pad
+// tokens have q=k=v=bias (image_encoder.py:168-172,227).  rel_h/rel_w: [2*win-1, hd] fp32.
+int encoder_attention(const __half* qkv, const float* qkv_bias, const float* rel_h,
+                      const float* rel_w, int B, int s, int win, int heads, int hd, __half* out,
+                      cudaStream_t st);
+
+// ---- TopoNet pieces (toponet.cu) -----------------------------------------------------------------------------
+// points dtype: 0 = float32, 1 = int64, 2 = int32 ; pairs dtype: 1 = int64, 2 = int32
+int topo_sample_features(const float* feat_nchw, int B, int C, int s, int P, const void* points,
+                         int pts_dtype, int N, __half* out, cudaStream_t st);
+int topo_pair_features(const float* pst, const float* w_off, const float* bias, const void* points,
+                       int pts_dtype, const void* pairs, int pairs_dtype, int B, int N, int Ns,
+                       int Np, int zero_offset, float* x32, __half* x16, cudaStream_t st);
+int topo_fix_valid(const uint8_t* valid, int rows, int Np, uint8_t* out, cudaStream_t st);
+int topo_attention(const __half* qkv, const uint8_t* valid, int rows, int Np, __half* out,
+                   cudaStream_t st);
+int topo_output(const float* x32, const uint8_t* valid_fixed, const float* w, const float* b,
+                int tokens, float* logits, float* scores, cudaStream_t st);
+
+// ---- mask fusion (kernels.cu) : inferencer.py:79-110 --------------------------------------------------------
+int fuse_masks(const float* scores, int n_tiles, int P, const int* tile_x0, const int* tile_y0,
+               int H, int W, uint8_t* keypoint_u8, uint8_t* road_u8, cudaStream_t st);
+
+}  // namespace srb
