@@ -1,0 +1,315 @@
+"""Drop-in `SAMRoad` for the tiled-inference hot path of htcr/sam_road, backed by libsamroad_b200.so.
+
+Mirrors the reference's model-level interface (reference model.py):
+    SAMRoad(config)                                              model.py:193
+    .load_state_dict(ckpt["state_dict"], strict=True)            inferencer.py:250-252
+    .forward(rgb, graph_points, pairs, valid)                    model.py:414-457
+    .infer_masks_and_img_features(rgb)                           model.py:459-495
+    .infer_toponet(image_embeddings, graph_points, pairs, valid) model.py:498-508
+with the same state_dict key set, argument meaning and output shapes/dtypes.
+
+Host side is Python/PyTorch only as plumbing (parameters, device memory, streams); all model math
+runs in the hand-written sm_100a kernels behind the C ABI (include/samroad_b200.h).  There is no
+PyTorch / CPU fallback: without the shared library or a CUDA device the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import warnings
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib
+
+_VIT = {  # model.py:198-218
+    "vit_b": (768, 12, 12, (2, 5, 8, 11)),
+    "vit_l": (1024, 24, 16, (5, 11, 17, 23)),
+    "vit_h": (1280, 32, 16, (7, 15, 23, 31)),
+}
+_TOPO_VERSION = {"no_offset": _lib.TOPO_NO_OFFSET, "no_transformer": _lib.TOPO_NO_TRANSFORMER}
+
+
+def _cfg_get(config, key, default=None):
+    """Config access that tolerates addict.Dict (missing key -> empty falsy Dict, utils.py:6-9),
+    plain dicts and attribute-style namespaces."""
+    if isinstance(config, dict):
+        v = config.get(key, default)
+    else:
+        v = getattr(config, key, default)
+    if v is None or (isinstance(v, dict) and len(v) == 0):
+        return default
+    return v
+
+
+def param_shapes(config) -> Dict[str, Tuple[int, ...]]:
+    """The reference's parameter names and shapes for this config."""
+    version = _cfg_get(config, "SAM_VERSION", "vit_b")
+    assert version in _VIT, f"SAM_VERSION must be one of {sorted(_VIT)}"   # model.py:197
+    D, depth, heads, glob = _VIT[version]
+    P = int(_cfg_get(config, "PATCH_SIZE"))
+    s, hd = P // 16, D // heads
+    lora = int(_cfg_get(config, "LORA_RANK", 0)) if _cfg_get(config, "ENCODER_LORA", False) else 0
+    sh: Dict[str, Tuple[int, ...]] = {}
+    e = "image_encoder."
+    sh[e + "pos_embed"] = (1, s, s, D)
+    sh[e + "patch_embed.proj.weight"] = (D, 3, 16, 16)
+    sh[e + "patch_embed.proj.bias"] = (D,)
+    for i in range(depth):
+        p = f"{e}blocks.{i}."
+        rows = 2 * s - 1 if i in glob else 2 * 14 - 1
+        sh[p + "norm1.weight"] = (D,); sh[p + "norm1.bias"] = (D,)
+        sh[p + "attn.rel_pos_h"] = (rows, hd); sh[p + "attn.rel_pos_w"] = (rows, hd)
+        sh[p + "attn.qkv.weight"] = (3 * D, D); sh[p + "attn.qkv.bias"] = (3 * D,)
+        if lora:
+            sh[p + "attn.qkv.linear_a_q.weight"] = (lora, D); sh[p + "attn.qkv.linear_b_q.weight"] = (D, lora)
+            sh[p + "attn.qkv.linear_a_v.weight"] = (lora, D); sh[p + "attn.qkv.linear_b_v.weight"] = (D, lora)
+        sh[p + "attn.proj.weight"] = (D, D); sh[p + "attn.proj.bias"] = (D,)
+        sh[p + "norm2.weight"] = (D,); sh[p + "norm2.bias"] = (D,)
+        sh[p + "mlp.lin1.weight"] = (4 * D, D); sh[p + "mlp.lin1.bias"] = (4 * D,)
+        sh[p + "mlp.lin2.weight"] = (D, 4 * D); sh[p + "mlp.lin2.bias"] = (D,)
+    sh[e + "neck.0.weight"] = (256, D, 1, 1)
+    sh[e + "neck.1.weight"] = (256,); sh[e + "neck.1.bias"] = (256,)
+    sh[e + "neck.2.weight"] = (256, 256, 3, 3)
+    sh[e + "neck.3.weight"] = (256,); sh[e + "neck.3.bias"] = (256,)
+    if _cfg_get(config, "USE_SAM_DECODER", False):
+        raise NotImplementedError(
+            "USE_SAM_DECODER: True (SAM TwoWayTransformer mask decoder, reference model.py:260-282) "
+            "is not built in sam_road_b200 yet; every shipped config/toponet_*.yaml uses the naive "
+            "map_decoder (USE_SAM_DECODER: False)")
+    for idx, (cin, cout) in zip((0, 3, 5, 7), ((256, 128), (128, 64), (64, 32), (32, 2))):
+        sh[f"map_decoder.{idx}.weight"] = (cin, cout, 2, 2)
+        sh[f"map_decoder.{idx}.bias"] = (cout,)
+    sh["map_decoder.1.weight"] = (128,); sh["map_decoder.1.bias"] = (128,)
+    t = "topo_net."
+    sh[t + "feature_proj.weight"] = (128, 256); sh[t + "feature_proj.bias"] = (128,)
+    sh[t + "pair_proj.weight"] = (128, 258); sh[t + "pair_proj.bias"] = (128,)
+    if _cfg_get(config, "TOPONET_VERSION", "normal") != "no_transformer":
+        for l in range(3):
+            p = f"{t}transformer_encoder.layers.{l}."
+            sh[p + "self_attn.in_proj_weight"] = (384, 128); sh[p + "self_attn.in_proj_bias"] = (384,)
+            sh[p + "self_attn.out_proj.weight"] = (128, 128); sh[p + "self_attn.out_proj.bias"] = (128,)
+            sh[p + "linear1.weight"] = (128, 128); sh[p + "linear1.bias"] = (128,)
+            sh[p + "linear2.weight"] = (128, 128); sh[p + "linear2.bias"] = (128,)
+            sh[p + "norm1.weight"] = (128,); sh[p + "norm1.bias"] = (128,)
+            sh[p + "norm2.weight"] = (128,); sh[p + "norm2.bias"] = (128,)
+    sh[t + "output_proj.weight"] = (1, 128); sh[t + "output_proj.bias"] = (1,)
+    return sh
+
+
+class _Node(nn.Module):
+    """Parameter container; nested so that state_dict() keys equal the reference's."""
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("parameter container, not callable")
+
+
+def _register(root: nn.Module, key: str, p: nn.Parameter) -> None:
+    parts = key.split(".")
+    node = root
+    for name in parts[:-1]:
+        if name not in node._modules:
+            node.add_module(name, _Node())
+        node = node._modules[name]
+    node.register_parameter(parts[-1], p)
+
+
+try:  # the reference derives from LightningModule (model.py:190); use it when importable
+    import lightning.pytorch as _pl
+    _Base = _pl.LightningModule
+except Exception:  # lightning is absent in this image; inference needs nothing Lightning-specific
+    _Base = nn.Module
+
+
+class SAMRoad(_Base):
+    """B200-native SAMRoad (inference only)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        if _cfg_get(config, "NO_SAM", False):
+            raise NotImplementedError(   # same behaviour as the reference (model.py:232-242)
+                "This ablation experiment depends on detectron2 and is not part of the release.")
+        self._shapes = param_shapes(config)
+        version = _cfg_get(config, "SAM_VERSION", "vit_b")
+        self._vit = _VIT[version]
+        self.image_size = int(_cfg_get(config, "PATCH_SIZE"))
+        gen = torch.Generator().manual_seed(0)
+        for key, shape in self._shapes.items():
+            if key.endswith("norm1.weight") or key.endswith("norm2.weight") or \
+                    key in ("image_encoder.neck.1.weight", "image_encoder.neck.3.weight",
+                            "map_decoder.1.weight"):
+                init = torch.ones(shape)
+            elif key.endswith(".bias") or "rel_pos" in key or key.endswith("pos_embed") or \
+                    "linear_b_" in key:
+                init = torch.zeros(shape)
+            else:
+                fan_in = 1
+                for d in shape[1:]:
+                    fan_in *= d
+                init = (torch.rand(shape, generator=gen) * 2 - 1) / max(1.0, fan_in) ** 0.5
+            _register(self, key, nn.Parameter(init, requires_grad=False))
+        self.register_buffer("pixel_mean", torch.tensor([123.675, 116.28, 103.53]).view(-1, 1, 1), False)
+        self.register_buffer("pixel_std", torch.tensor([58.395, 57.12, 57.375]).view(-1, 1, 1), False)
+        self._handles: Dict[int, int] = {}     # cuda device index -> samroad_handle_t
+        self._weights_version = 0
+        self._synced_version: Dict[int, int] = {}
+        self.matched_param_names = set()
+        ckpt_path = _cfg_get(config, "SAM_CKPT_PATH", None)
+        if ckpt_path and os.path.isfile(str(ckpt_path)):
+            self._load_sam_checkpoint(str(ckpt_path))   # model.py:367-390
+
+    # ---- weights -----------------------------------------------------------------------------
+    def _load_sam_checkpoint(self, path: str) -> None:
+        """Initialise from a SAM checkpoint like model.py:367-411: resize pos_embed and the global
+        blocks' rel-pos tables to this tile size, then load every name+shape match (non-strict)."""
+        import torch.nn.functional as F
+        sd = torch.load(path, map_location="cpu")
+        s = self.image_size // 16
+        glob = self._vit[3]
+        if "image_encoder.pos_embed" in sd and sd["image_encoder.pos_embed"].shape[1] != s:
+            pe = sd["image_encoder.pos_embed"].permute(0, 3, 1, 2)
+            sd["image_encoder.pos_embed"] = F.interpolate(
+                pe, (s, s), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+            for i in glob:
+                for ax in ("h", "w"):
+                    k = f"image_encoder.blocks.{i}.attn.rel_pos_{ax}"
+                    if k in sd:
+                        t = sd[k][None, None]
+                        sd[k] = F.interpolate(t, (2 * s - 1, t.shape[-1]), mode="bilinear",
+                                              align_corners=False)[0, 0]
+        own = dict(self.named_parameters())
+        matched = {k: v for k, v in sd.items() if k in own and own[k].shape == v.shape}
+        self.matched_param_names = set(matched)
+        self.load_state_dict(matched, strict=False)
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        out = super().load_state_dict(state_dict, strict=strict, **kw)
+        self._weights_version += 1
+        return out
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self._weights_version += 1
+        return out
+
+    def mark_weights_dirty(self) -> None:
+        """Call after mutating parameters in place so the packed device weights are rebuilt."""
+        self._weights_version += 1
+
+    def _handle(self, device: torch.device) -> int:
+        if device.type != "cuda":
+            raise RuntimeError(
+                f"sam_road_b200.SAMRoad runs on CUDA (sm_100a) only; got input on '{device}'. "
+                "There is no CPU path.")
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        lib = _lib.load()
+        if idx not in self._handles:
+            D, depth, heads, glob = self._vit
+            cfg = _lib.SamRoadCfg()
+            cfg.patch_size, cfg.embed_dim, cfg.depth, cfg.num_heads = self.image_size, D, depth, heads
+            cfg.window_size = 14
+            for i, g in enumerate(glob):
+                cfg.global_attn_indexes[i] = g
+            cfg.use_sam_decoder = 1 if _cfg_get(self.config, "USE_SAM_DECODER", False) else 0
+            cfg.toponet_version = _TOPO_VERSION.get(
+                _cfg_get(self.config, "TOPONET_VERSION", "normal"), _lib.TOPO_NORMAL)
+            cfg.lora_rank = (int(_cfg_get(self.config, "LORA_RANK", 0))
+                             if _cfg_get(self.config, "ENCODER_LORA", False) else 0)
+            h = C.c_void_p()
+            _lib.check(lib.samroad_create(C.byref(cfg), idx, C.byref(h)), "samroad_create")
+            self._handles[idx] = h.value
+        if self._synced_version.get(idx) != self._weights_version:
+            h = self._handles[idx]
+            for key, p in self.named_parameters():
+                t = p.detach().to(device="cpu", dtype=torch.float32).contiguous()
+                shape = (C.c_int64 * t.dim())(*t.shape)
+                _lib.check(lib.samroad_load_tensor(h, key.encode(), t.data_ptr(), shape, t.dim()),
+                           f"samroad_load_tensor({key})")
+            _lib.check(lib.samroad_finalize_weights(h), "samroad_finalize_weights")
+            self._synced_version[idx] = self._weights_version
+        return self._handles[idx]
+
+    def __del__(self):
+        try:
+            lib = _lib.load()
+            for h in self._handles.values():
+                lib.samroad_destroy(h)
+        except Exception:
+            pass
+
+    # ---- inference entry points ----------------------------------------------------------------------
+    @staticmethod
+    def _prep_rgb(rgb: torch.Tensor):
+        if rgb.dtype == torch.uint8:
+            return rgb.contiguous(), _lib.U8
+        return rgb.to(torch.float32).contiguous(), _lib.F32
+
+    def _encode(self, rgb: torch.Tensor, want_logits: bool):
+        if rgb.dim() != 4 or rgb.shape[-1] != 3 or rgb.shape[1] != self.image_size or \
+                rgb.shape[2] != self.image_size:
+            raise ValueError(f"rgb must be [B,{self.image_size},{self.image_size},3], got "
+                             f"{tuple(rgb.shape)}")
+        h = self._handle(rgb.device)
+        B, P, s = rgb.shape[0], self.image_size, self.image_size // 16
+        x, dt = self._prep_rgb(rgb)
+        scores = torch.empty((B, P, P, 2), dtype=torch.float32, device=rgb.device)
+        logits = torch.empty_like(scores) if want_logits else None
+        emb = torch.empty((B, 256, s, s), dtype=torch.float32, device=rgb.device)
+        if B > 0:
+            with torch.cuda.device(rgb.device):
+                _lib.check(_lib.load().samroad_encode_masks(
+                    h, x.data_ptr(), dt, B, scores.data_ptr(), _lib.ptr(logits), emb.data_ptr(),
+                    _lib.current_stream_ptr()), "samroad_encode_masks")
+        return scores, logits, emb
+
+    def _topo(self, image_embeddings, graph_points, pairs, valid, want_logits: bool):
+        dev = image_embeddings.device
+        h = self._handle(dev)
+        B, Ns, Np = pairs.shape[0], pairs.shape[1], pairs.shape[2]
+        N = graph_points.shape[1]
+        emb = image_embeddings.to(torch.float32).contiguous()
+        if graph_points.dtype == torch.int64:
+            pts, pdt = graph_points.contiguous(), _lib.I64
+        elif graph_points.dtype == torch.int32:
+            pts, pdt = graph_points.contiguous(), _lib.I32
+        else:
+            pts, pdt = graph_points.to(torch.float32).contiguous(), _lib.F32
+        if pairs.dtype == torch.int32:
+            prs, qdt = pairs.contiguous(), _lib.I32
+        else:
+            prs, qdt = pairs.to(torch.int64).contiguous(), _lib.I64
+        val = valid.to(torch.bool).contiguous().view(torch.uint8)
+        scores = torch.empty((B, Ns, Np, 1), dtype=torch.float32, device=dev)
+        logits = torch.empty_like(scores) if want_logits else None
+        if B * Ns * Np > 0:
+            with torch.cuda.device(dev):
+                _lib.check(_lib.load().samroad_toponet(
+                    h, emb.data_ptr(), pts.to(dev).data_ptr(), pdt, prs.to(dev).data_ptr(), qdt,
+                    val.to(dev).data_ptr(), B, N, Ns, Np, _lib.ptr(logits), scores.data_ptr(),
+                    _lib.current_stream_ptr()), "samroad_toponet")
+        return logits, scores
+
+    @torch.no_grad()
+    def forward(self, rgb, graph_points, pairs, valid):
+        """(mask_logits[B,H,W,2], mask_scores[B,H,W,2], topo_logits[B,Ns,Np,1], topo_scores) --
+        model.py:414-457.  Inference only: no autograd graph is produced."""
+        scores, logits, emb = self._encode(rgb, True)
+        t_logits, t_scores = self._topo(emb, graph_points, pairs, valid, True)
+        return logits, scores, t_logits, t_scores
+
+    @torch.no_grad()
+    def infer_masks_and_img_features(self, rgb):
+        """(mask_scores[B,H,W,2], image_embeddings[B,256,H/16,W/16]) -- model.py:459-495."""
+        scores, _, emb = self._encode(rgb, False)
+        return scores, emb
+
+    @torch.no_grad()
+    def infer_toponet(self, image_embeddings, graph_points, pairs, valid):
+        """topo_scores[B,Ns,Np,1] -- model.py:498-508."""
+        return self._topo(image_embeddings, graph_points, pairs, valid, False)[1]
+
+    def training_step(self, *a, **k):
+        raise NotImplementedError("sam_road_b200.SAMRoad is inference-only (SURVEY.md §8b)")

@@ -1,0 +1,175 @@
+"""End-to-end parity of the CUDA path (through SAMRoad -> ctypes -> C ABI) against the fp32 oracle
+on seeded synthetic weights and inputs.  Tolerance (BASELINE.json north_star): mask-logit and
+topology-logit max-abs <= 1e-3 with the reference's default-scale weights; the achieved numbers
+are written to gpurun_out/parity_report.json.
+
+The oracle runs in fp32 on the GPU (TF32 disabled) so that ViT-B@512 finishes in seconds; it is the
+same code the CPU suite pins against the reference's golden fixtures."""
+import json
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import samroad_oracle as O, synth  # noqa: E402
+from sam_road_b200 import SAMRoad  # noqa: E402
+
+DEV = "cuda:0"
+TOL_LOGIT = 1e-3
+_REPORT = {}
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _fp32_oracle_math(report_dir):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    path = os.path.join(report_dir, "parity_report.json")
+    old = {}
+    if os.path.exists(path):
+        try:
+            old = json.load(open(path))
+        except Exception:
+            old = {}
+    old.update(_REPORT)
+    json.dump(old, open(path, "w"), indent=1, sort_keys=True)
+
+
+def _config(patch, version="vit_b", topo="normal", lora=0):
+    return dict(SAM_VERSION=version, PATCH_SIZE=patch, USE_SAM_DECODER=False,
+                ENCODER_LORA=lora > 0, LORA_RANK=lora, TOPONET_VERSION=topo, NO_SAM=False)
+
+
+def _build(cfg, seed=0, gain=1.0):
+    spec = O.ModelSpec.from_config(cfg)
+    sd = synth.make_state_dict(spec, seed=seed, logit_gain=gain)
+    net = SAMRoad(cfg)
+    net.load_state_dict(sd, strict=True)
+    net.eval().to(DEV)
+    sd_dev = {k: v.to(DEV) for k, v in sd.items()}
+    return spec, sd_dev, net
+
+
+def _maxabs(a, b):
+    return (a.float() - b.float()).abs().max().item()
+
+
+@pytest.mark.parametrize("name,patch,version,B,lora", [
+    ("vitb_256", 256, "vit_b", 3, 0),
+    ("vitb_512", 512, "vit_b", 2, 0),
+    ("vitb_256_lora4", 256, "vit_b", 1, 4),
+    ("vith_256", 256, "vit_h", 1, 0),
+])
+def test_encode_and_topo_parity(name, patch, version, B, lora):
+    cfg = _config(patch, version, lora=lora)
+    spec, sd, net = _build(cfg)
+    rgb_u8 = synth.make_tiles(B, patch, seed=3).to(DEV)
+    rgb = rgb_u8.float()
+    with torch.no_grad():
+        o_scores, o_feat, o_logits = O.infer_masks_and_img_features(sd, spec, rgb, return_logits=True)
+    pts, prs, val = [t.to(DEV) for t in synth.make_topo_inputs(B, patch, 48, seed=4)]
+    with torch.no_grad():
+        o_ts, o_tl = O.infer_toponet(sd, spec, o_feat, pts, prs, val, return_logits=True)
+
+    scores, feat = net.infer_masks_and_img_features(rgb)
+    assert scores.shape == o_scores.shape and feat.shape == o_feat.shape
+    assert scores.dtype == torch.float32 and feat.dtype == torch.float32
+    scores_u8, feat_u8 = net.infer_masks_and_img_features(rgb_u8)     # uint8 input extension
+    assert torch.equal(scores, scores_u8) and torch.equal(feat, feat_u8)
+
+    logits, scores2, t_logits, t_scores = net(rgb, pts, prs, val)
+    assert torch.equal(scores2, scores)
+    t_scores2 = net.infer_toponet(feat, pts, prs, val)
+    assert torch.equal(t_scores2, t_scores)
+    # TopoNet alone on the oracle's own embeddings (isolates TopoNet error from encoder error)
+    t_scores_iso = net.infer_toponet(o_feat, pts, prs, val)
+    vmask = val.unsqueeze(-1)
+    rep = {
+        "feat_maxabs": _maxabs(feat, o_feat), "feat_absmax": o_feat.abs().max().item(),
+        "mask_logit_maxabs": _maxabs(logits, o_logits),
+        "mask_logit_range": [o_logits.min().item(), o_logits.max().item()],
+        "mask_score_maxabs": _maxabs(scores, o_scores),
+        "topo_logit_maxabs_valid": ((t_logits - o_tl).abs() * vmask).max().item(),
+        "topo_logit_maxabs_all": _maxabs(t_logits, o_tl),
+        "topo_logit_range": [o_tl.min().item(), o_tl.max().item()],
+        "topo_score_maxabs_valid": ((t_scores - o_ts).abs() * vmask).max().item(),
+        "topo_score_iso_maxabs_valid": ((t_scores_iso - o_ts).abs() * vmask).max().item(),
+        "tolerance_logit": TOL_LOGIT,
+    }
+    _REPORT[name] = rep
+    print(name, json.dumps(rep))
+    assert torch.isfinite(logits).all() and torch.isfinite(t_logits).all()
+    assert rep["mask_logit_maxabs"] <= TOL_LOGIT, rep
+    assert rep["topo_logit_maxabs_all"] <= TOL_LOGIT, rep
+    assert rep["mask_score_maxabs"] <= TOL_LOGIT and rep["topo_score_maxabs_valid"] <= TOL_LOGIT
+
+
+def test_parity_with_wide_logits():
+    """Same check with the last decoder layer / output_proj scaled so logits span several units
+    (random init only gives +-0.5): relative tolerance 2e-3 of the logit range."""
+    cfg = _config(256)
+    spec, sd, net = _build(cfg, seed=1, gain=12.0)
+    rgb = synth.make_tiles(2, 256, seed=5).to(DEV).float()
+    pts, prs, val = [t.to(DEV) for t in synth.make_topo_inputs(2, 256, 64, seed=6)]
+    with torch.no_grad():
+        o = O.forward(sd, spec, rgb, pts, prs, val)
+    r = net(rgb, pts, prs, val)
+    span_m = (o[0].max() - o[0].min()).item()
+    span_t = (o[2].max() - o[2].min()).item()
+    em, et = _maxabs(r[0], o[0]), _maxabs(r[2], o[2])
+    _REPORT["vitb_256_gain12"] = {"mask_logit_maxabs": em, "mask_logit_span": span_m,
+                                  "topo_logit_maxabs": et, "topo_logit_span": span_t}
+    print(_REPORT["vitb_256_gain12"])
+    assert em <= 2e-3 * span_m and et <= 2e-3 * span_t
+
+
+@pytest.mark.parametrize("topo", ["no_offset", "no_transformer", "no_tgt_features"])
+def test_toponet_versions(topo):
+    cfg = _config(256, topo=topo)
+    spec, sd, net = _build(cfg, seed=2)
+    feat = torch.randn(2, 256, 16, 16, device=DEV)
+    pts, prs, val = [t.to(DEV) for t in synth.make_topo_inputs(2, 256, 30, seed=8)]
+    with torch.no_grad():
+        o_ts, o_tl = O.infer_toponet(sd, spec, feat, pts, prs, val, return_logits=True)
+    ts = net.infer_toponet(feat, pts, prs, val)
+    assert _maxabs(ts, o_ts) <= TOL_LOGIT
+
+
+def test_toponet_edge_cases():
+    """float32 / int32 inputs, all-invalid rows (flipped to valid, model.py:128-130), border points
+    x = P (legal: the rtree box query is inclusive), empty batch."""
+    cfg = _config(256)
+    spec, sd, net = _build(cfg, seed=3)
+    feat = torch.randn(2, 256, 16, 16, device=DEV)
+    pts, prs, val = synth.make_topo_inputs(2, 256, 20, seed=9)
+    pts[0, 0] = torch.tensor([256, 256])
+    pts[1, 1] = torch.tensor([0, 256])
+    val[0, 3] = False
+    val[1, :] = False
+    pts, prs, val = pts.to(DEV), prs.to(DEV), val.to(DEV)
+    with torch.no_grad():
+        o_ts = O.infer_toponet(sd, spec, feat, pts, prs, val)
+        o_tsf = O.infer_toponet(sd, spec, feat, pts.float() + 0.25, prs, val)
+    assert _maxabs(net.infer_toponet(feat, pts, prs, val), o_ts) <= TOL_LOGIT
+    assert _maxabs(net.infer_toponet(feat, pts.int(), prs.int(), val), o_ts) <= TOL_LOGIT
+    assert _maxabs(net.infer_toponet(feat, pts.float() + 0.25, prs, val), o_tsf) <= TOL_LOGIT
+    empty = net.infer_toponet(feat, pts[:, :0], prs[:, :0], val[:, :0])
+    assert empty.shape == (2, 0, 16, 1)
+    s0, f0 = net.infer_masks_and_img_features(torch.zeros((0, 256, 256, 3), device=DEV))
+    assert s0.shape == (0, 256, 256, 2) and f0.shape == (0, 256, 16, 16)
+
+
+def test_non_contiguous_and_errors():
+    cfg = _config(256)
+    spec, sd, net = _build(cfg, seed=4)
+    base = synth.make_tiles(2, 256, seed=10).to(DEV).float()
+    view = base.permute(0, 3, 1, 2).contiguous().permute(0, 2, 3, 1)    # non-contiguous NHWC view
+    a = net.infer_masks_and_img_features(base)
+    b = net.infer_masks_and_img_features(view)
+    assert torch.equal(a[0], b[0])
+    with pytest.raises(ValueError):
+        net.infer_masks_and_img_features(torch.zeros(1, 128, 128, 3, device=DEV))
+    with pytest.raises(RuntimeError):
+        net.infer_masks_and_img_features(torch.zeros(1, 256, 256, 3))    # CPU tensor: no fallback
