@@ -96,6 +96,22 @@ int samroad_fuse_masks(const float* scores, int n_tiles, int P, const int32_t* t
 int samroad_encode_masks_host(samroad_handle_t h, const void* rgb_host, int rgb_dtype, int B,
                               float* mask_scores_host, float* image_embeddings_host);
 
+/* One whole batch with HOST buffers: uploads tiles (and TopoNet inputs), runs encoder + mask head
+ * (+ TopoNet when points_host != NULL), downloads mask scores [B,P,P,2], image embeddings
+ * [B,256,s,s] and topology scores [B,Ns,Np], then synchronises.  Any output may be NULL.  This is
+ * the call the benchmark's `e2e` figure times (what inferencer.py:87-104,195-206 does per batch). */
+int samroad_infer_batch_host(samroad_handle_t h, const void* rgb_host, int rgb_dtype, int B,
+                             const void* points_host, int pts_dtype, const void* pairs_host,
+                             int pairs_dtype, const uint8_t* valid_host, int N, int Ns, int Np,
+                             float* mask_scores_host, float* image_embeddings_host,
+                             float* topo_scores_host);
+
+/* Per-kernel-class CUDA-event timing on the launching stream (bench.py's roofline numbers).
+ * samroad_timing_enable(h, 1) clears and starts recording; samroad_timing_read() synchronises and
+ * writes a JSON object {"<class>": {"launches","ms","flops","bytes"}, ...} into buf. */
+int samroad_timing_enable(samroad_handle_t h, int on);
+int samroad_timing_read(samroad_handle_t h, char* buf, size_t cap);
+
 /* Activation workspace the handle needs for a batch of B tiles (bytes). */
 size_t samroad_workspace_bytes(samroad_handle_t h, int B);
 

@@ -43,6 +43,9 @@ SIGNATURES = {
     "samroad_toponet": (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "samroad_fuse_masks": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "samroad_encode_masks_host": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "samroad_infer_batch_host": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "samroad_timing_enable": (_i, [_vp, _i]),
+    "samroad_timing_read": (_i, [_vp, C.c_char_p, C.c_size_t]),
     "samroad_workspace_bytes": (C.c_size_t, [_vp, _i]),
     "samroad_launch_count": (C.c_uint64, [_i]),
     "samroad_last_error": (C.c_char_p, []),

@@ -53,8 +53,48 @@ struct TopoLayerW {
 
 }  // namespace
 
+// Per-kernel-class CUDA-event timing (bench.py roofline): events are recorded on the launching
+// stream around every launch while enabled; totals are read back with samroad_timing_read().
+struct KernelTimer {
+  struct Rec { int tag; double flops; double bytes; cudaEvent_t a, b; };
+  bool on = false;
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  cudaEvent_t get() {
+    if (used == pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      pool.push_back(e);
+    }
+    return pool[used++];
+  }
+  void begin(int tag, double flops, double bytes, cudaStream_t st) {
+    if (!on) return;
+    Rec r{tag, flops, bytes, get(), get()};
+    cudaEventRecord(r.a, st);
+    recs.push_back(r);
+  }
+  void end(cudaStream_t st) {
+    if (!on) return;
+    cudaEventRecord(recs.back().b, st);
+  }
+  void reset() { recs.clear(); used = 0; }
+};
+
+enum KTag {
+  KT_PATCH_IM2COL = 0, KT_GEMM_PATCH, KT_LAYERNORM, KT_GEMM_QKV, KT_ATTN_WINDOW, KT_ATTN_GLOBAL,
+  KT_GEMM_PROJ, KT_GEMM_LIN1, KT_GEMM_LIN2, KT_NECK, KT_DECODER, KT_TOPO_SAMPLE, KT_TOPO_GEMM,
+  KT_TOPO_PAIR, KT_TOPO_ATTN, KT_TOPO_OUT, KT_COUNT
+};
+static const char* kTagNames[KT_COUNT] = {
+  "patch_im2col", "gemm_patch_embed", "layernorm", "gemm_qkv", "attention_window",
+  "attention_global", "gemm_proj", "gemm_mlp_lin1", "gemm_mlp_lin2", "neck", "map_decoder",
+  "topo_sample", "topo_gemm", "topo_pair_features", "topo_attention", "topo_output"};
+
 struct samroad_ctx {
   SamRoadCfg cfg;
+  KernelTimer timer;
   int device = 0;
   int s = 0, T = 0, D = 0, hd = 0;
   bool finalized = false;
@@ -277,6 +317,15 @@ TopoWs layout_topo(int B, int N, int Ns, int Np, void* base) {
   w.total = off;
   return w;
 }
+
+// run a launcher with optional CUDA-event timing under a kernel-class tag
+#define SRB_T(tag, flops, bytes, expr)                                   \
+  do {                                                                   \
+    h->timer.begin((tag), (double)(flops), (double)(bytes), st);         \
+    int _rc = (expr);                                                    \
+    h->timer.end(st);                                                    \
+    if (_rc != 0) return _rc;                                            \
+  } while (0)
 
 #define SRB_TRY(expr)            \
   do {                           \
@@ -553,41 +602,66 @@ extern "C" int samroad_encode_masks(samroad_handle_t h, const void* rgb, int rgb
 
   // patch embed + pos embed  (image_encoder.py:107-109, 387-395; normalisation model.py:465-467)
   const float inv_std[3] = {1.0f / kPixelStd[0], 1.0f / kPixelStd[1], 1.0f / kPixelStd[2]};
-  SRB_TRY(im2col_patch16(rgb, rgb_dtype == SAMROAD_U8 ? 1 : 0, B, P, kPixelMean, inv_std, w.XN, st));
-  SRB_TRY(gemm_f32out(w.XN, 768, h->pe_w, 768, M, D, 768, h->pe_b, nullptr, h->pos, T, w.X, D, st));
+  const double Md = M, Dd = D;
+  const double px_bytes = static_cast<double>(B) * P * P * 3 * (rgb_dtype == SAMROAD_U8 ? 1 : 4);
+  SRB_T(KT_PATCH_IM2COL, 0, px_bytes + Md * 768 * 2,
+        im2col_patch16(rgb, rgb_dtype == SAMROAD_U8 ? 1 : 0, B, P, kPixelMean, inv_std, w.XN, st));
+  SRB_T(KT_GEMM_PATCH, 2 * Md * Dd * 768, Md * 768 * 2 + Md * Dd * 4,
+        gemm_f32out(w.XN, 768, h->pe_w, 768, M, D, 768, h->pe_b, nullptr, h->pos, T, w.X, D, st));
 
   // transformer blocks (image_encoder.py:166-182)
   for (int i = 0; i < h->cfg.depth; ++i) {
     const BlockW& b = h->blocks[i];
-    SRB_TRY(layernorm_f16(w.X, b.ln1_g, b.ln1_b, 1e-6f, M, D, w.XN, st));
-    SRB_TRY(gemm_f16out(w.XN, D, b.qkv_w, D, M, 3 * D, D, b.qkv_b, ACT_NONE, w.QKV, 3 * D, st));
-    SRB_TRY(encoder_attention(w.QKV, b.qkv_b, b.rel_h, b.rel_w, B, s, b.win, h->cfg.num_heads,
-                              h->hd, w.ATT, st));
-    SRB_TRY(gemm_f32out(w.ATT, D, b.proj_w, D, M, D, D, b.proj_b, w.X, nullptr, 0, w.X, D, st));
-    SRB_TRY(layernorm_f16(w.X, b.ln2_g, b.ln2_b, 1e-6f, M, D, w.XN, st));
-    SRB_TRY(gemm_f16out(w.XN, D, b.lin1_w, D, M, 4 * D, D, b.lin1_b, ACT_GELU, w.H, 4 * D, st));
-    SRB_TRY(gemm_f32out(w.H, 4 * D, b.lin2_w, 4 * D, M, D, 4 * D, b.lin2_b, w.X, nullptr, 0, w.X, D,
-                        st));
+    // algorithmic attention FLOPs: real query/key tokens only
+    double att_flops = 0;
+    {
+      const int nw = (s + b.win - 1) / b.win;
+      for (int wy = 0; wy < nw; ++wy)
+        for (int wx = 0; wx < nw; ++wx) {
+          const double ry = (wy + 1) * b.win <= s ? b.win : s - wy * b.win;
+          const double rx = (wx + 1) * b.win <= s ? b.win : s - wx * b.win;
+          att_flops += 4.0 * (ry * rx) * (ry * rx) * h->hd;
+        }
+      att_flops *= static_cast<double>(B) * h->cfg.num_heads;
+    }
+    SRB_T(KT_LAYERNORM, 0, Md * Dd * 6, layernorm_f16(w.X, b.ln1_g, b.ln1_b, 1e-6f, M, D, w.XN, st));
+    SRB_T(KT_GEMM_QKV, 2 * Md * 3 * Dd * Dd, Md * Dd * 2 + Md * 3 * Dd * 2,
+          gemm_f16out(w.XN, D, b.qkv_w, D, M, 3 * D, D, b.qkv_b, ACT_NONE, w.QKV, 3 * D, st));
+    SRB_T(b.win == s ? KT_ATTN_GLOBAL : KT_ATTN_WINDOW, att_flops, Md * 4 * Dd * 2,
+          encoder_attention(w.QKV, b.qkv_b, b.rel_h, b.rel_w, B, s, b.win, h->cfg.num_heads, h->hd,
+                            w.ATT, st));
+    SRB_T(KT_GEMM_PROJ, 2 * Md * Dd * Dd, Md * Dd * 2 + Md * Dd * 8,
+          gemm_f32out(w.ATT, D, b.proj_w, D, M, D, D, b.proj_b, w.X, nullptr, 0, w.X, D, st));
+    SRB_T(KT_LAYERNORM, 0, Md * Dd * 6, layernorm_f16(w.X, b.ln2_g, b.ln2_b, 1e-6f, M, D, w.XN, st));
+    SRB_T(KT_GEMM_LIN1, 2 * Md * 4 * Dd * Dd, Md * Dd * 2 + Md * 4 * Dd * 2,
+          gemm_f16out(w.XN, D, b.lin1_w, D, M, 4 * D, D, b.lin1_b, ACT_GELU, w.H, 4 * D, st));
+    SRB_T(KT_GEMM_LIN2, 2 * Md * 4 * Dd * Dd, Md * 4 * Dd * 2 + Md * Dd * 8,
+          gemm_f32out(w.H, 4 * D, b.lin2_w, 4 * D, M, D, 4 * D, b.lin2_b, w.X, nullptr, 0, w.X, D,
+                      st));
   }
 
   // neck (image_encoder.py:88-104,114): 1x1 conv -> LN2d -> 3x3 conv -> LN2d
-  SRB_TRY(convert_f32_f16(w.X, static_cast<long>(M) * D, w.XN, st));
-  SRB_TRY(gemm_ln(w.XN, D, h->neck0_w, D, M, 256, D, nullptr, nullptr, h->neck1_g, h->neck1_b,
-                  1e-6f, 256, ACT_NONE, w.N1, nullptr, nullptr, T, 256, st));
+  SRB_T(KT_NECK, 0, Md * Dd * 6, convert_f32_f16(w.X, static_cast<long>(M) * D, w.XN, st));
+  SRB_T(KT_NECK, 2 * Md * 256 * Dd, Md * Dd * 2 + Md * 256 * 2,
+        gemm_ln(w.XN, D, h->neck0_w, D, M, 256, D, nullptr, nullptr, h->neck1_g, h->neck1_b, 1e-6f,
+                256, ACT_NONE, w.N1, nullptr, nullptr, T, 256, st));
   __half* IM2 = w.H;
-  SRB_TRY(im2col_3x3(w.N1, B, s, 256, IM2, st));
-  SRB_TRY(gemm_ln(IM2, 2304, h->neck2_w, 2304, M, 256, 2304, nullptr, nullptr, h->neck3_g,
-                  h->neck3_b, 1e-6f, 256, ACT_NONE, w.FEAT, nullptr, image_embeddings, T, 256, st));
+  SRB_T(KT_NECK, 0, Md * 256 * 2 * 10, im2col_3x3(w.N1, B, s, 256, IM2, st));
+  SRB_T(KT_NECK, 2 * Md * 256 * 2304, Md * 2304 * 2 + Md * 256 * 6,
+        gemm_ln(IM2, 2304, h->neck2_w, 2304, M, 256, 2304, nullptr, nullptr, h->neck3_g, h->neck3_b,
+                1e-6f, 256, ACT_NONE, w.FEAT, nullptr, image_embeddings, T, 256, st));
 
   // naive map decoder (model.py:286-295, 490-491) as three GEMMs, pixel shuffle by row indexing
   if (mask_scores || mask_logits) {
-    SRB_TRY(gemm_ln(w.FEAT, 256, h->dec1_w, 256, M, 512, 256, h->dec1_b, nullptr, h->dec_ln_g,
-                    h->dec_ln_b, 1e-6f, 128, ACT_GELU, w.D1, nullptr, nullptr, T, 512, st));
+    SRB_T(KT_DECODER, 2 * Md * 512 * 256, Md * 256 * 2 + Md * 512 * 2,
+          gemm_ln(w.FEAT, 256, h->dec1_w, 256, M, 512, 256, h->dec1_b, nullptr, h->dec_ln_g,
+                  h->dec_ln_b, 1e-6f, 128, ACT_GELU, w.D1, nullptr, nullptr, T, 512, st));
     __half* D2 = w.H;
-    SRB_TRY(gemm_f16out(w.D1, 128, h->dec2_w, 128, 4 * M, 256, 128, h->dec2_b, ACT_GELU, D2, 256,
-                        st));
-    SRB_TRY(gemm_dec_final(D2, 64, h->dec3_w, 64, 16 * M, 64, h->dec3_b, h->dec4_w, h->dec4_b, s, P,
-                           mask_scores, mask_logits, st));
+    SRB_T(KT_DECODER, 2 * Md * 4 * 256 * 128, Md * 512 * 2 + Md * 1024 * 2,
+          gemm_f16out(w.D1, 128, h->dec2_w, 128, 4 * M, 256, 128, h->dec2_b, ACT_GELU, D2, 256, st));
+    SRB_T(KT_DECODER, 2 * Md * 16 * (128 * 64 + 4 * 32 * 8), Md * 1024 * 2 + Md * 512 * 4,
+          gemm_dec_final(D2, 64, h->dec3_w, 64, 16 * M, 64, h->dec3_b, h->dec4_w, h->dec4_b, s, P,
+                         mask_scores, mask_logits, st));
   }
   return 0;
 }
@@ -647,30 +721,40 @@ extern "C" int samroad_toponet(samroad_handle_t h, const float* image_embeddings
   const int zero_off = h->cfg.toponet_version == SAMROAD_TOPO_NO_OFFSET;
   const bool no_tf = h->cfg.toponet_version == SAMROAD_TOPO_NO_TRANSFORMER;
 
-  SRB_TRY(topo_sample_features(image_embeddings, B, 256, h->s, h->cfg.patch_size, points, pts_dtype,
-                               N, w.F16, st));
-  SRB_TRY(gemm_f16out(w.F16, 256, h->tp_feat_w, 256, pts, 128, 256, h->tp_feat_b, ACT_RELU, w.PF16,
-                      128, st));
-  SRB_TRY(gemm_f32out(w.PF16, 128, h->tp_st_w, 128, pts, 256, 128, nullptr, nullptr, nullptr, 0,
-                      w.PST, 256, st));
-  SRB_TRY(topo_fix_valid(valid, rows, Np, w.VF, st));
-  SRB_TRY(topo_pair_features(w.PST, h->tp_off_w, h->tp_pair_b, points, pts_dtype, pairs,
-                             pairs_dtype, B, N, Ns, Np, zero_off, w.X32, w.X16, st));
+  const double ptsd = pts, tokd = tok;
+  SRB_T(KT_TOPO_SAMPLE, 0, ptsd * 256 * (16 + 2),
+        topo_sample_features(image_embeddings, B, 256, h->s, h->cfg.patch_size, points, pts_dtype, N,
+                             w.F16, st));
+  SRB_T(KT_TOPO_GEMM, 2 * ptsd * 128 * 256, ptsd * 384 * 2,
+        gemm_f16out(w.F16, 256, h->tp_feat_w, 256, pts, 128, 256, h->tp_feat_b, ACT_RELU, w.PF16, 128,
+                    st));
+  SRB_T(KT_TOPO_GEMM, 2 * ptsd * 256 * 128, ptsd * (256 + 1024),
+        gemm_f32out(w.PF16, 128, h->tp_st_w, 128, pts, 256, 128, nullptr, nullptr, nullptr, 0, w.PST,
+                    256, st));
+  SRB_T(KT_TOPO_PAIR, 0, tokd * 2, topo_fix_valid(valid, rows, Np, w.VF, st));
+  SRB_T(KT_TOPO_PAIR, tokd * 128 * 6, tokd * 128 * (8 + 6),
+        topo_pair_features(w.PST, h->tp_off_w, h->tp_pair_b, points, pts_dtype, pairs, pairs_dtype, B,
+                           N, Ns, Np, zero_off, w.X32, w.X16, st));
   if (!no_tf) {
     for (int l = 0; l < 3; ++l) {
       const TopoLayerW& t = h->tp_layers[l];
-      SRB_TRY(gemm_f16out(w.X16, 128, t.in_w, 128, tok, 384, 128, t.in_b, ACT_NONE, w.QKV16, 384,
-                          st));
-      SRB_TRY(topo_attention(w.QKV16, w.VF, rows, Np, w.ATT16, st));
-      SRB_TRY(gemm_ln(w.ATT16, 128, t.out_w, 128, tok, 128, 128, t.out_b, w.X32, t.n1_g, t.n1_b,
-                      1e-5f, 128, ACT_NONE, w.X16, w.X32, nullptr, 1, 128, st));
-      SRB_TRY(gemm_f16out(w.X16, 128, t.l1_w, 128, tok, 128, 128, t.l1_b, ACT_RELU, w.H16, 128, st));
-      SRB_TRY(gemm_ln(w.H16, 128, t.l2_w, 128, tok, 128, 128, t.l2_b, w.X32, t.n2_g, t.n2_b, 1e-5f,
-                      128, ACT_NONE, w.X16, w.X32, nullptr, 1, 128, st));
+      SRB_T(KT_TOPO_GEMM, 2 * tokd * 384 * 128, tokd * 512 * 2,
+            gemm_f16out(w.X16, 128, t.in_w, 128, tok, 384, 128, t.in_b, ACT_NONE, w.QKV16, 384, st));
+      SRB_T(KT_TOPO_ATTN, 4 * tokd * Np * 128, tokd * 512 * 2,
+            topo_attention(w.QKV16, w.VF, rows, Np, w.ATT16, st));
+      SRB_T(KT_TOPO_GEMM, 2 * tokd * 128 * 128, tokd * 128 * (2 + 4 + 4 + 2),
+            gemm_ln(w.ATT16, 128, t.out_w, 128, tok, 128, 128, t.out_b, w.X32, t.n1_g, t.n1_b, 1e-5f,
+                    128, ACT_NONE, w.X16, w.X32, nullptr, 1, 128, st));
+      SRB_T(KT_TOPO_GEMM, 2 * tokd * 128 * 128, tokd * 128 * 4,
+            gemm_f16out(w.X16, 128, t.l1_w, 128, tok, 128, 128, t.l1_b, ACT_RELU, w.H16, 128, st));
+      SRB_T(KT_TOPO_GEMM, 2 * tokd * 128 * 128, tokd * 128 * (2 + 4 + 4 + 2),
+            gemm_ln(w.H16, 128, t.l2_w, 128, tok, 128, 128, t.l2_b, w.X32, t.n2_g, t.n2_b, 1e-5f, 128,
+                    ACT_NONE, w.X16, w.X32, nullptr, 1, 128, st));
     }
   }
-  SRB_TRY(topo_output(w.X32, no_tf ? nullptr : w.VF, h->tp_out_w, h->tp_out_b, tok, topo_logits,
-                      topo_scores, st));
+  SRB_T(KT_TOPO_OUT, 2 * tokd * 128, tokd * (512 + 8),
+        topo_output(w.X32, no_tf ? nullptr : w.VF, h->tp_out_w, h->tp_out_b, tok, topo_logits,
+                    topo_scores, st));
   return 0;
 }
 
@@ -683,6 +767,97 @@ extern "C" int samroad_fuse_masks(const float* scores, int n_tiles, int P, const
   SRB_REQUIRE(scores && tile_x0 && tile_y0 && keypoint_u8 && road_u8, "samroad_fuse_masks: null");
   return fuse_masks(scores, n_tiles, P, tile_x0, tile_y0, H, W, keypoint_u8, road_u8,
                     static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int samroad_timing_enable(samroad_handle_t h, int on) {
+  SRB_REQUIRE(h != nullptr, "null samroad handle");
+  SRB_CUDA_OK(cudaSetDevice(h->device));
+  SRB_CUDA_OK(cudaDeviceSynchronize());
+  h->timer.reset();
+  h->timer.on = on != 0;
+  return 0;
+}
+
+// Writes one JSON object {"<kernel class>": {"launches": n, "ms": total, "flops": f, "bytes": b}, ...}
+// for everything recorded since samroad_timing_enable(h, 1); synchronises the device.
+extern "C" int samroad_timing_read(samroad_handle_t h, char* buf, size_t cap) {
+  SRB_REQUIRE(h != nullptr && buf != nullptr && cap > 2, "samroad_timing_read: bad arguments");
+  SRB_CUDA_OK(cudaSetDevice(h->device));
+  SRB_CUDA_OK(cudaDeviceSynchronize());
+  double ms[KT_COUNT] = {0}, fl[KT_COUNT] = {0}, by[KT_COUNT] = {0};
+  long cnt[KT_COUNT] = {0};
+  for (const auto& r : h->timer.recs) {
+    float t = 0.f;
+    SRB_CUDA_OK(cudaEventElapsedTime(&t, r.a, r.b));
+    ms[r.tag] += t; fl[r.tag] += r.flops; by[r.tag] += r.bytes; cnt[r.tag] += 1;
+  }
+  size_t off = 0;
+  off += snprintf(buf + off, cap - off, "{");
+  bool first = true;
+  for (int t = 0; t < KT_COUNT && off + 200 < cap; ++t) {
+    if (cnt[t] == 0) continue;
+    off += snprintf(buf + off, cap - off,
+                    "%s\"%s\": {\"launches\": %ld, \"ms\": %.6f, \"flops\": %.6e, \"bytes\": %.6e}",
+                    first ? "" : ", ", kTagNames[t], cnt[t], ms[t], fl[t], by[t]);
+    first = false;
+  }
+  snprintf(buf + off, cap - off, "}");
+  return 0;
+}
+
+// One whole batch with HOST buffers: H2D tiles (+ TopoNet inputs), encoder + mask head + TopoNet,
+// D2H of mask scores, image embeddings and topology scores, then synchronise.  Any output may be
+// NULL; TopoNet is skipped when points_host is NULL.
+extern "C" int samroad_infer_batch_host(samroad_handle_t h, const void* rgb_host, int rgb_dtype,
+                                        int B, const void* points_host, int pts_dtype,
+                                        const void* pairs_host, int pairs_dtype,
+                                        const uint8_t* valid_host, int N, int Ns, int Np,
+                                        float* mask_scores_host, float* image_embeddings_host,
+                                        float* topo_scores_host) {
+  SRB_TRY(check_handle(h, true));
+  SRB_REQUIRE(rgb_host, "samroad_infer_batch_host: null rgb");
+  if (B <= 0) return 0;
+  const size_t P = h->cfg.patch_size, s = h->s;
+  const size_t in_bytes = static_cast<size_t>(B) * P * P * 3 * (rgb_dtype == SAMROAD_U8 ? 1 : 4);
+  const size_t sc_bytes = static_cast<size_t>(B) * P * P * 2 * 4;
+  const size_t em_bytes = static_cast<size_t>(B) * 256 * s * s * 4;
+  const bool topo = points_host && pairs_host && valid_host && Ns > 0 && N > 0;
+  const size_t pt_sz = pts_dtype == SAMROAD_I64 ? 8 : 4, pr_sz = pairs_dtype == SAMROAD_I64 ? 8 : 4;
+  const size_t pts_bytes = topo ? static_cast<size_t>(B) * N * 2 * pt_sz : 0;
+  const size_t prs_bytes = topo ? static_cast<size_t>(B) * Ns * Np * 2 * pr_sz : 0;
+  const size_t val_bytes = topo ? static_cast<size_t>(B) * Ns * Np : 0;
+  const size_t ts_bytes = topo ? static_cast<size_t>(B) * Ns * Np * 4 : 0;
+  const size_t o_pts = align_up(in_bytes, 256), o_prs = o_pts + align_up(pts_bytes, 256);
+  const size_t o_val = o_prs + align_up(prs_bytes, 256), o_ts = o_val + align_up(val_bytes, 256);
+  SRB_TRY(ensure_bytes(&h->stage_in, &h->stage_in_bytes, o_ts + align_up(ts_bytes, 256)));
+  SRB_TRY(ensure_bytes(reinterpret_cast<void**>(&h->stage_scores), &h->stage_scores_bytes, sc_bytes));
+  SRB_TRY(ensure_bytes(reinterpret_cast<void**>(&h->stage_emb), &h->stage_emb_bytes, em_bytes));
+  char* base = static_cast<char*>(h->stage_in);
+  cudaStream_t st = nullptr;
+  SRB_CUDA_OK(cudaMemcpyAsync(base, rgb_host, in_bytes, cudaMemcpyHostToDevice, st));
+  if (topo) {
+    SRB_CUDA_OK(cudaMemcpyAsync(base + o_pts, points_host, pts_bytes, cudaMemcpyHostToDevice, st));
+    SRB_CUDA_OK(cudaMemcpyAsync(base + o_prs, pairs_host, prs_bytes, cudaMemcpyHostToDevice, st));
+    SRB_CUDA_OK(cudaMemcpyAsync(base + o_val, valid_host, val_bytes, cudaMemcpyHostToDevice, st));
+  }
+  SRB_TRY(samroad_encode_masks(h, base, rgb_dtype, B, mask_scores_host ? h->stage_scores : nullptr,
+                               nullptr, h->stage_emb, st));
+  if (mask_scores_host)
+    SRB_CUDA_OK(cudaMemcpyAsync(mask_scores_host, h->stage_scores, sc_bytes, cudaMemcpyDeviceToHost,
+                                st));
+  if (image_embeddings_host)
+    SRB_CUDA_OK(cudaMemcpyAsync(image_embeddings_host, h->stage_emb, em_bytes,
+                                cudaMemcpyDeviceToHost, st));
+  if (topo) {
+    SRB_TRY(samroad_toponet(h, h->stage_emb, base + o_pts, pts_dtype, base + o_prs, pairs_dtype,
+                            reinterpret_cast<const uint8_t*>(base + o_val), B, N, Ns, Np, nullptr,
+                            reinterpret_cast<float*>(base + o_ts), st));
+    if (topo_scores_host)
+      SRB_CUDA_OK(cudaMemcpyAsync(topo_scores_host, base + o_ts, ts_bytes, cudaMemcpyDeviceToHost,
+                                  st));
+  }
+  SRB_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
 }
 
 extern "C" uint64_t samroad_launch_count(int reset) { return launch_count(reset != 0); }

@@ -13,7 +13,8 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-from oracle import samroad_oracle as O, synth  # noqa: E402
+from oracle import samroad_oracle as O  # noqa: E402
+from sam_road_b200 import synth  # noqa: E402
 from sam_road_b200 import SAMRoad  # noqa: E402
 
 DEV = "cuda:0"
@@ -44,7 +45,7 @@ def _config(patch, version="vit_b", topo="normal", lora=0):
 
 def _build(cfg, seed=0, gain=1.0):
     spec = O.ModelSpec.from_config(cfg)
-    sd = synth.make_state_dict(spec, seed=seed, logit_gain=gain)
+    sd = synth.make_state_dict(cfg, seed=seed, logit_gain=gain)
     net = SAMRoad(cfg)
     net.load_state_dict(sd, strict=True)
     net.eval().to(DEV)
