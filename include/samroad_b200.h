@@ -144,6 +144,10 @@ int samroad_op_attention(const void* qkv16, const float* qkv_bias, const float* 
                          const float* rel_w, int B, int s, int win, int heads, int head_dim,
                          void* out16, void* stream);
 
+/* Test hook: route samroad_op_attention / the encoder through the fp32 SIMT attention kernel (the
+ * independent on-device checker of the tcgen05 kernel).  Not for production use. */
+void samroad_debug_force_simt_attention(int on);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,8 +13,11 @@
 // v1: fp32 SIMT flash-style kernel (one thread = one query row, keys streamed through shared memory
 // in chunks of 32 with an online softmax).  It is the straightforward, easily-audited statement of
 // the math and the on-device checker for the tensor-core version.
+#include "attention_tc.cuh"
 #include "common.cuh"
 #include "ops.h"
+
+#define SRB_TRY_RC(expr) do { int _rc = (expr); if (_rc != 0) return _rc; } while (0)
 
 namespace srb {
 
@@ -196,11 +199,90 @@ static int launch_attention_simt(const __half* qkv, const float* qkv_bias, const
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// rel-pos table packing for the tensor-core kernel: tab[r] = rel_pos_h[r] for r < 2K-1,
+// rel_pos_w[r - rows/2] for rows/2 <= r < rows/2 + 2K-1, 0 otherwise; fp16 [rows, 64]
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_rel_table_kernel(const float* __restrict__ rel_h, const float* __restrict__ rel_w,
+                                      int win, int hd, int rows, __half* __restrict__ tab) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * hd) return;
+  const int r = idx / hd, c = idx % hd, L = 2 * win - 1;
+  float v = 0.f;
+  if (r < L) v = rel_h[r * hd + c];
+  else if (r >= rows / 2 && r < rows / 2 + L) v = rel_w[(r - rows / 2) * hd + c];
+  tab[idx] = __float2half_rn(v);
+}
+
+int pack_rel_table(const float* rel_h, const float* rel_w, int win, int hd, __half* tab,
+                   cudaStream_t st) {
+  const int rows = rel_table_rows(win);
+  pack_rel_table_kernel<<<(rows * hd + 255) / 256, 256, 0, st>>>(rel_h, rel_w, win, hd, rows, tab);
+  SRB_CUDA_OK(cudaGetLastError());
+  note_launch();
+  return 0;
+}
+
+static bool g_force_simt = false;
+void attention_force_simt(bool on) { g_force_simt = on; }
+
+template <bool kWindow, int WIN>
+static int launch_attention_tc(const __half* qkv, const float* qkv_bias, const __half* tab, int B,
+                               int s, int heads, __half* out, cudaStream_t st) {
+  const int D = heads * 64;
+  const int T = s * s;
+  CUtensorMap tmQKV, tmTab;
+  if (kWindow) {
+    const uint64_t dims[4] = {static_cast<uint64_t>(3 * D), static_cast<uint64_t>(s),
+                              static_cast<uint64_t>(s), static_cast<uint64_t>(B)};
+    const uint64_t strides[3] = {static_cast<uint64_t>(3 * D), static_cast<uint64_t>(s) * 3 * D,
+                                 static_cast<uint64_t>(T) * 3 * D};
+    const uint32_t box[4] = {64, static_cast<uint32_t>(WIN), static_cast<uint32_t>(WIN), 1};
+    if (int rc = make_tmap_f16_4d(&tmQKV, qkv, dims, strides, box)) return rc;
+  } else {
+    if (int rc = make_tmap_f16_2d(&tmQKV, qkv, static_cast<uint64_t>(B) * T, 3 * D, 3 * D, 128))
+      return rc;
+  }
+  const int rows = rel_table_rows(WIN);
+  if (int rc = make_tmap_f16_2d(&tmTab, tab, rows, 64, 64, rows)) return rc;
+  auto kern = attention_tc_kernel<kWindow, WIN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kAtcSmemBytes));
+    attr_set = true;
+  }
+  AtcParams p;
+  p.qkv_bias = qkv_bias; p.out = out; p.B = B; p.s = s; p.heads = heads; p.D = D;
+  p.nwin = kWindow ? (s + WIN - 1) / WIN : 1;
+  p.scale = 0.125f;
+  const int units = kWindow ? B * p.nwin * p.nwin * heads : B * (T / 256) * heads;
+  kern<<<units, kAtcThreads, kAtcSmemBytes, st>>>(tmQKV, tmTab, p);
+  SRB_CUDA_OK(cudaGetLastError());
+  note_launch();
+  return 0;
+}
+
 int encoder_attention(const __half* qkv, const float* qkv_bias, const float* rel_h,
-                      const float* rel_w, int B, int s, int win, int heads, int hd, __half* out,
-                      cudaStream_t st) {
+                      const float* rel_w, const __half* rel_tab, int B, int s, int win, int heads,
+                      int hd, __half* out, cudaStream_t st) {
   SRB_REQUIRE(win > 0 && win <= s && s <= 64, "attention: win=%d s=%d unsupported", win, s);
   if (B <= 0) return 0;
+  // tensor-core path: head_dim 64; window 14 on any grid, global on 16x16 / 32x32 token grids
+  const bool tc_ok = hd == 64 && !g_force_simt &&
+                     ((win == 14 && s >= 14) || (win == s && (s == 16 || s == 32)));
+  if (tc_ok) {
+    const __half* tab = rel_tab;
+    if (!tab) {
+      static __half* scratch = nullptr;   // op-level calls without a pre-packed table
+      if (!scratch) SRB_CUDA_OK(cudaMalloc(&scratch, 128 * 64 * sizeof(__half)));
+      SRB_TRY_RC(pack_rel_table(rel_h, rel_w, win, hd, scratch, st));
+      tab = scratch;
+    }
+    if (win == 14 && win < s) return launch_attention_tc<true, 14>(qkv, qkv_bias, tab, B, s, heads, out, st);
+    if (s == 16) return launch_attention_tc<false, 16>(qkv, qkv_bias, tab, B, s, heads, out, st);
+    return launch_attention_tc<false, 32>(qkv, qkv_bias, tab, B, s, heads, out, st);
+  }
   if (hd == 64) return launch_attention_simt<64>(qkv, qkv_bias, rel_h, rel_w, B, s, win, heads, out, st);
   if (hd == 80) return launch_attention_simt<80>(qkv, qkv_bias, rel_h, rel_w, B, s, win, heads, out, st);
   set_last_error("attention: head_dim=%d unsupported (64 or 80)", hd);

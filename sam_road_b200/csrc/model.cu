@@ -38,6 +38,7 @@ struct BlockW {
   __half* qkv_w;  float* qkv_b;
   __half* proj_w; float* proj_b;
   float *rel_h, *rel_w;
+  __half* rel_tab;   // packed [rel_pos_h ; rel_pos_w] fp16 table for the tensor-core attention
   __half* lin1_w; float* lin1_b;
   __half* lin2_w; float* lin2_b;
   int win;   // attention window (14) or s for global blocks
@@ -479,6 +480,18 @@ extern "C" int samroad_finalize_weights(samroad_handle_t h) {
     b.proj_b = P.f32(K("attn.proj.bias"), {D});
     b.rel_h = P.f32(K("attn.rel_pos_h"), {rel_rows, hd});
     b.rel_w = P.f32(K("attn.rel_pos_w"), {rel_rows, hd});
+    b.rel_tab = nullptr;
+    if (P.ok && hd == 64) {   // [rows, 64] fp16 table consumed by attention_tc_kernel
+      void* d = nullptr;
+      if (cudaMalloc(&d, 128 * 64 * sizeof(__half)) != cudaSuccess) {
+        P.fail("cudaMalloc of rel-pos table failed");
+      } else {
+        h->weight_allocs.push_back(d);
+        b.rel_tab = static_cast<__half*>(d);
+        if (pack_rel_table(b.rel_h, b.rel_w, b.win, static_cast<int>(hd), b.rel_tab, nullptr) != 0)
+          P.fail("pack_rel_table failed: %s", get_last_error());
+      }
+    }
     b.lin1_w = P.linear_w(K("mlp.lin1.weight"), 4 * D, D);
     b.lin1_b = P.f32(K("mlp.lin1.bias"), {4 * D});
     b.lin2_w = P.linear_w(K("mlp.lin2.weight"), D, 4 * D);
@@ -628,8 +641,8 @@ extern "C" int samroad_encode_masks(samroad_handle_t h, const void* rgb, int rgb
     SRB_T(KT_GEMM_QKV, 2 * Md * 3 * Dd * Dd, Md * Dd * 2 + Md * 3 * Dd * 2,
           gemm_f16out(w.XN, D, b.qkv_w, D, M, 3 * D, D, b.qkv_b, ACT_NONE, w.QKV, 3 * D, st));
     SRB_T(b.win == s ? KT_ATTN_GLOBAL : KT_ATTN_WINDOW, att_flops, Md * 4 * Dd * 2,
-          encoder_attention(w.QKV, b.qkv_b, b.rel_h, b.rel_w, B, s, b.win, h->cfg.num_heads, h->hd,
-                            w.ATT, st));
+          encoder_attention(w.QKV, b.qkv_b, b.rel_h, b.rel_w, b.rel_tab, B, s, b.win,
+                            h->cfg.num_heads, h->hd, w.ATT, st));
     SRB_T(KT_GEMM_PROJ, 2 * Md * Dd * Dd, Md * Dd * 2 + Md * Dd * 8,
           gemm_f32out(w.ATT, D, b.proj_w, D, M, D, D, b.proj_b, w.X, nullptr, 0, w.X, D, st));
     SRB_T(KT_LAYERNORM, 0, Md * Dd * 6, layernorm_f16(w.X, b.ln2_g, b.ln2_b, 1e-6f, M, D, w.XN, st));
@@ -897,7 +910,8 @@ extern "C" int samroad_op_layernorm(const float* x, const float* gamma, const fl
 extern "C" int samroad_op_attention(const void* qkv16, const float* qkv_bias, const float* rel_h,
                                     const float* rel_w, int B, int s, int win, int heads,
                                     int head_dim, void* out16, void* stream) {
-  return encoder_attention(static_cast<const __half*>(qkv16), qkv_bias, rel_h, rel_w, B, s, win,
-                           heads, head_dim, static_cast<__half*>(out16),
+  return encoder_attention(static_cast<const __half*>(qkv16), qkv_bias, rel_h, rel_w, nullptr, B, s,
+                           win, heads, head_dim, static_cast<__half*>(out16),
                            static_cast<cudaStream_t>(stream));
 }
+extern "C" void samroad_debug_force_simt_attention(int on) { attention_force_simt(on != 0); }

@@ -47,9 +47,17 @@ int convert_f32_f16(const float* x, long n, __half* out, cudaStream_t st);
 // qkv: [B*s*s, 3*D] fp16, columns (q|k|v) x head x hd ; out: [B*s*s, D] fp16.
 // win == s means global attention; otherwise window attention over zero-padded LN output, whose pad
 // tokens have q=k=v=bias (image_encoder.py:168-172,227).  rel_h/rel_w: [2*win-1, hd] fp32.
+// rel_tab (optional): fp16 [64 or 128, 64] = [rel_pos_h ; rel_pos_w ; 0] as packed by
+// pack_rel_table(); when null the launcher packs it on the fly into a per-device scratch.
 int encoder_attention(const __half* qkv, const float* qkv_bias, const float* rel_h,
-                      const float* rel_w, int B, int s, int win, int heads, int hd, __half* out,
-                      cudaStream_t st);
+                      const float* rel_w, const __half* rel_tab, int B, int s, int win, int heads,
+                      int hd, __half* out, cudaStream_t st);
+// rows of the packed table for a window size (64 if 4*win-2 <= 64 else 128)
+inline int rel_table_rows(int win) { return 4 * win - 2 <= 64 ? 64 : 128; }
+int pack_rel_table(const float* rel_h, const float* rel_w, int win, int hd, __half* tab,
+                   cudaStream_t st);
+// force the SIMT v1 attention kernel (tests use it as the independent on-device checker)
+void attention_force_simt(bool on);
 
 // ---- TopoNet pieces (toponet.cu) -----------------------------------------------------------------------------
 // points dtype: 0 = float32, 1 = int64, 2 = int32 ; pairs dtype: 1 = int64, 2 = int32
