@@ -190,5 +190,9 @@ def test_attention_tc_vs_simt(B, s, win):
         outs.append(out.float())
     lib.samroad_debug_force_simt_attention(0)
     err = (outs[0] - outs[1]).abs().max().item()
+    mean_err = (outs[0] - outs[1]).abs().mean().item()
+    mag = outs[0].abs().max().item()
+    print(f"tc vs simt: max err {err:.3e} mean err {mean_err:.3e} |out|max {mag:.3f}")
     assert torch.isfinite(outs[1]).all()
-    assert err < 3e-3, err
+    # P is rounded to fp16 (rel 2^-11) before the PV MMA and the output to fp16: a few output ulps
+    assert err <= 2.5e-3 * mag and mean_err <= 2e-4 * mag, (err, mean_err, mag)
