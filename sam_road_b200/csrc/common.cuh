@@ -76,20 +76,22 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
-// Faster erf-GELU for GEMM epilogues whose output is rounded to fp16 anyway.
-// erf via Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7 abs), one ex2 + one rcp.
+// Fast erf-GELU for GEMM epilogues: gelu(x) = relu(x) - |x| * 0.5*erfc(|x|/sqrt2), with
+// log2(0.5*erfc(a/sqrt2)) fitted by a degree-6 polynomial on [0, 5.6] (clamped beyond, where the term
+// is < 1e-8).  6 FMA + 1 MUFU.EX2 + 3 ALU; max abs error 2.5e-7, i.e. <0.04 half-ulps of the fp16 the
+// result is rounded to (fit + error scan: DESIGN.md "GELU").
 __device__ __forceinline__ float gelu_erf_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  const float e = exp2f(-z * z * 1.4426950408889634f);
-  const float erf_abs = fmaf(-p, e, 1.0f);          // erf(|x|/sqrt2)
-  const float erf_v = copysignf(erf_abs, x);
-  return 0.5f * x * (1.0f + erf_v);
+  const float a = fabsf(x);
+  const float ac = fminf(a, 5.6f);
+  float l = fmaf(3.45301887136884e-05f, ac, -0.0007803441258147359f);
+  l = fmaf(l, ac, 0.008112940937280655f);
+  l = fmaf(l, ac, -0.05345592275261879f);
+  l = fmaf(l, ac, -0.45874229073524475f);
+  l = fmaf(l, ac, -1.1512099504470825f);
+  l = fmaf(l, ac, -0.999992311000824f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(l));
+  return fmaf(-a, e, fmaxf(x, 0.0f));
 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }

@@ -5,7 +5,12 @@
 //
 //   warp 0      : TMA producer   (cp.async.bulk.tensor, 128B-swizzled 128x64 / BNx64 boxes)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16)
-//   warps 2..5  : epilogue       (tcgen05.ld 32x32b -> registers -> fused math -> global)
+//   warps 2..9  : epilogue       (tcgen05.ld 32x32b -> registers -> fused math -> global); two warps
+//                 per TMEM lane quarter split the tile's columns.  Streaming epilogues (EpiF16 /
+//                 EpiF32) transpose each 32x32 fp32 block through a per-warp smem scratch so that
+//                 global loads/stores are row-contiguous (8 lanes x 16 B per row) instead of one
+//                 row per lane; row-statistics epilogues (EpiLN, EpiDecFinal) keep one row per
+//                 thread and use four warps.
 //
 // Persistent CTAs (grid = min(#tiles, #SMs)), STAGES-deep smem ring between TMA and MMA, and a
 // two-deep TMEM accumulator ring between MMA and epilogue so the epilogue of tile i overlaps the
@@ -28,7 +33,9 @@ namespace srb {
 
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;
+constexpr int kGemmEpiWarps = 8;
+constexpr int kGemmScratchFloats = 32 * 33;   // per epilogue warp: 32x32 fp32 block, padded rows
 
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -51,55 +58,69 @@ struct TmemRow {
 };
 
 // ------------------------------------------------------------------------------------------------
-// Epilogue 1: out16[m,n] = act(acc + bias[n])                       (qkv, MLP lin1, TopoNet lin)
+// Streaming epilogues.  A warp owns 32 tile rows (its TMEM lane quarter) x n_cols columns.  Per
+// 32-column chunk: lane r holds row r's 32 accumulators -> scratch[r][0..31] (row stride 33 floats,
+// conflict-free) -> re-read as "lane l holds columns 4*(l&7).. of row 4*j + (l>>3)", j = 0..7 ->
+// bias / activation / residual in that layout -> 8 lanes cover 128 (fp32) or 64 (fp16) contiguous
+// bytes of a row per store instruction.
 // ------------------------------------------------------------------------------------------------
+template <class F>
+__device__ __forceinline__ void epi_stream_chunks(int n_cols, const TmemRow& row, float* scratch,
+                                                  int lane, F&& body) {
+  const int nchunks = n_cols >> 5;
+  const int cc = (lane & 7) * 4, rsub = lane >> 3;
+  for (int c = 0; c < nchunks; ++c) {
+    float v[32];
+    row.load(c, v);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) scratch[lane * 33 + i] = v[i];
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int rr = 4 * j + rsub;
+      const float* sp = scratch + rr * 33 + cc;
+      body(c, rr, cc, make_float4(sp[0], sp[1], sp[2], sp[3]));
+    }
+    __syncwarp();
+  }
+}
+
+// Epilogue 1: out16[m,n] = act(acc + bias[n])                       (qkv, MLP lin1, TopoNet lin)
 struct EpiF16 {
+  static constexpr bool kSplitCols = true;
   struct Params {
     __half* out;          // [M, ldo]
     const float* bias;    // [N] or null
     int ldo;
     int act;
   };
-  static __device__ __forceinline__ void run(const Params& p, int m, bool valid, int n_base,
-                                             int n_cols, const TmemRow& row) {
-    const int nchunks = n_cols >> 5;
-    for (int c = 0; c < nchunks; ++c) {
-      float v[32];
-      row.load(c, v);
-      const int n0 = n_base + c * 32;
+  static __device__ __forceinline__ void run(const Params& p, int m0, int M, int n_base, int n_cols,
+                                             const TmemRow& row, float* scratch, int lane) {
+    epi_stream_chunks(n_cols, row, scratch, lane, [&](int c, int rr, int cc, float4 x) {
+      const int n = n_base + c * 32 + cc;
       if (p.bias) {
-        const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 b = __ldg(b4 + i);
-          v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-        }
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+        x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
       }
       if (p.act != ACT_NONE) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
+        x.x = apply_act(x.x, p.act); x.y = apply_act(x.y, p.act);
+        x.z = apply_act(x.z, p.act); x.w = apply_act(x.w, p.act);
       }
-      if (valid) {
-        uint4* o = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(m) * p.ldo + n0);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 u;
-          u.x = pack_half2(v[8 * i + 0], v[8 * i + 1]);
-          u.y = pack_half2(v[8 * i + 2], v[8 * i + 3]);
-          u.z = pack_half2(v[8 * i + 4], v[8 * i + 5]);
-          u.w = pack_half2(v[8 * i + 6], v[8 * i + 7]);
-          o[i] = u;
-        }
+      const int m = m0 + rr;
+      if (m < M) {
+        uint2 u;
+        u.x = pack_half2(x.x, x.y);
+        u.y = pack_half2(x.z, x.w);
+        *reinterpret_cast<uint2*>(p.out + static_cast<size_t>(m) * p.ldo + n) = u;
       }
-    }
+    });
   }
 };
 
-// ------------------------------------------------------------------------------------------------
 // Epilogue 2: out32[m,n] = acc + bias[n] + resid[m,n] + pos[m % pos_rows, n]
 //             (patch-embed + pos_embed, attention proj + shortcut, MLP lin2 + shortcut; plain f32)
-// ------------------------------------------------------------------------------------------------
 struct EpiF32 {
+  static constexpr bool kSplitCols = true;
   struct Params {
     float* out;           // [M, ldo]
     const float* bias;    // [N] or null
@@ -109,47 +130,29 @@ struct EpiF32 {
     int pos_rows;
     int n_total;
   };
-  static __device__ __forceinline__ void run(const Params& p, int m, bool valid, int n_base,
-                                             int n_cols, const TmemRow& row) {
-    const int nchunks = n_cols >> 5;
-    const float* posrow =
-        p.pos ? p.pos + static_cast<size_t>(m % p.pos_rows) * p.n_total : nullptr;
-    for (int c = 0; c < nchunks; ++c) {
-      float v[32];
-      row.load(c, v);
-      const int n0 = n_base + c * 32;
+  static __device__ __forceinline__ void run(const Params& p, int m0, int M, int n_base, int n_cols,
+                                             const TmemRow& row, float* scratch, int lane) {
+    epi_stream_chunks(n_cols, row, scratch, lane, [&](int c, int rr, int cc, float4 x) {
+      const int n = n_base + c * 32 + cc;
+      const int m = m0 + rr;
+      if (m >= M) return;
       if (p.bias) {
-        const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 b = __ldg(b4 + i);
-          v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-        }
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+        x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
       }
-      if (valid) {
-        if (posrow) {
-          const float4* q4 = reinterpret_cast<const float4*>(posrow + n0);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 b = __ldg(q4 + i);
-            v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-          }
-        }
-        float4* o = reinterpret_cast<float4*>(p.out + static_cast<size_t>(m) * p.ldo + n0);
-        if (p.resid) {
-          const float4* r4 =
-              reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(m) * p.ldo + n0);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 b = r4[i];
-            v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          o[i] = make_float4(v[4 * i + 0], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      if (p.pos) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(
+            p.pos + static_cast<size_t>(m % p.pos_rows) * p.n_total + n));
+        x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
       }
-    }
+      float* o = p.out + static_cast<size_t>(m) * p.ldo + n;
+      if (p.resid) {
+        const float4 b =
+            *reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(m) * p.ldo + n);
+        x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+      }
+      *reinterpret_cast<float4*>(o) = x;
+    });
   }
 };
 
@@ -161,6 +164,7 @@ struct EpiF32 {
 // fp32 NCHW ([b, n, tok] with tok = m % tokens, b = m / tokens) for the API-visible embeddings.
 // ------------------------------------------------------------------------------------------------
 struct EpiLN {
+  static constexpr bool kSplitCols = false;
   struct Params {
     __half* out16;        // [M, ldo] or null
     float* out32;         // [M, ldo] or null
@@ -197,8 +201,10 @@ struct EpiLN {
       }
     }
   }
-  static __device__ __forceinline__ void run(const Params& p, int m, bool valid, int n_base,
-                                             int n_cols, const TmemRow& row) {
+  static __device__ __forceinline__ void run(const Params& p, int m0, int M, int n_base, int n_cols,
+                                             const TmemRow& row, float* /*scratch*/, int lane) {
+    const int m = m0 + lane;
+    const bool valid = m < M;
     const int cpg = p.group >> 5;              // chunks per group
     const int ngroups = n_cols / p.group;
     const float inv_g = 1.0f / static_cast<float>(p.group);
@@ -273,6 +279,7 @@ struct EpiLN {
 // d = di*2 + dj (see decoder weight packing in pack.cu).
 // ------------------------------------------------------------------------------------------------
 struct EpiDecFinal {
+  static constexpr bool kSplitCols = false;
   struct Params {
     float* scores;        // [B, P, P, 2] or null
     float* logits;        // [B, P, P, 2] or null
@@ -282,8 +289,10 @@ struct EpiDecFinal {
     int s;                // feature map side (P/16)
     int P;
   };
-  static __device__ __forceinline__ void run(const Params& p, int m, bool valid, int n_base,
-                                             int n_cols, const TmemRow& row) {
+  static __device__ __forceinline__ void run(const Params& p, int m0, int M, int n_base, int n_cols,
+                                             const TmemRow& row, float* /*scratch*/, int lane) {
+    const int m = m0 + lane;
+    const bool valid = m < M;
     // decode pixel hierarchy of this row
     const int d2 = m & 3, d1 = (m >> 2) & 3;
     const int pix = m >> 4;
@@ -337,7 +346,8 @@ struct GemmSmem {
   static constexpr int kBBytes = BN * kGemmBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarOffset = STAGES * kStageBytes;
-  static constexpr int kTotal = kBarOffset + 256 + 1024;   // barriers + alignment slack
+  static constexpr int kScratchOffset = kBarOffset + 256;
+  static constexpr int kTotal = kScratchOffset + kGemmEpiWarps * kGemmScratchFloats * 4 + 1024;
 };
 
 template <int BN, int STAGES, class Epi>
@@ -372,7 +382,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], Epi::kSplitCols ? 8 : 4);
     }
     fence_barrier_init();
   }
@@ -433,25 +443,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===================== epilogue warps =====================
-    const int q = warp & 3;   // TMEM lane quarter this warp may access
-    int as = 0;
-    uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / num_n, n_blk = tile % num_n;
-      mbar_wait(&tfull_bar[as], aphase);
-      tc_fence_after_sync();
-      const int m = m_blk * kGemmBM + q * 32 + lane;
-      const int n_base = n_blk * BN;
-      const int n_cols = min(BN, N - n_base);
-      TmemRow row{tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                  static_cast<uint32_t>(as * BN)};
-      Epi::run(ep, m, m < M, n_base, n_cols, row);
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
-      as ^= 1;
-      if (as == 0) aphase ^= 1u;
+    // ===================== epilogue warps (2..9) =====================
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;  // which half of the tile's columns (streaming epilogues)
+    if (Epi::kSplitCols || half == 0) {
+      float* scratch = reinterpret_cast<float*>(smem + SM::kScratchOffset) +
+                       (warp - 2) * kGemmScratchFloats;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after_sync();
+        const int m0 = m_blk * kGemmBM + q * 32;
+        const int n_tile = min(BN, N - n_blk * BN);        // valid columns of this tile
+        int col0 = 0, n_cols = n_tile;
+        if (Epi::kSplitCols) {
+          col0 = half * (BN / 2);
+          n_cols = max(0, min(BN / 2, n_tile - col0));
+        }
+        TmemRow row{tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                    static_cast<uint32_t>(as * BN + col0)};
+        Epi::run(ep, m0, M, n_blk * BN + col0, n_cols, row, scratch, lane);
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        as ^= 1;
+        if (as == 0) aphase ^= 1u;
+      }
     }
   }
 
