@@ -384,8 +384,11 @@ def fuse_masks(tile_scores: Sequence[np.ndarray], tiles, H: int, W: int):
     return (kp * 255).to(torch.uint8).numpy(), (road * 255).to(torch.uint8).numpy()
 
 
-def infer_one_img(sd: StateDict, spec: ModelSpec, img: np.ndarray, config) -> tuple:
-    """Whole-scene driver (inferencer.py:61-234) on top of the oracle model."""
+def infer_one_img(sd: StateDict, spec: ModelSpec, img: np.ndarray, config, masks_override=None,
+                  return_edge_scores: bool = False) -> tuple:
+    """Whole-scene driver (inferencer.py:61-234) on top of the oracle model.  `masks_override`
+    (kp_mask, road_mask) lets a test continue from given fused masks; `return_edge_scores` also
+    returns {(src,tgt): mean score} before thresholding."""
     from collections import defaultdict
     H = img.shape[0]
     bs = int(config["INFER_BATCH_SIZE"])
@@ -397,10 +400,12 @@ def infer_one_img(sd: StateDict, spec: ModelSpec, img: np.ndarray, config) -> tu
         rgb = torch.stack([torch.tensor(img[y0:y1, x0:x1, :], dtype=torch.float32)
                            for _, (x0, y0), (x1, y1) in batch], 0)
         with torch.no_grad():
-            sc, ft = infer_masks_and_img_features(sd, spec, rgb)
+            sc, ft = infer_masks_and_img_features(sd, spec, rgb.to(next(iter(sd.values())).device))
         feats.append(ft)
-        scores_all.extend([s.numpy() for s in sc])
+        scores_all.extend([s.cpu().numpy() for s in sc])
     kp_mask, road_mask = fuse_masks(scores_all, tiles, img.shape[0], img.shape[1])
+    if masks_override is not None:
+        kp_mask, road_mask = masks_override
     gp = extract_graph_points(kp_mask, road_mask, float(config["ITSC_THRESHOLD"]),
                               float(config["ROAD_THRESHOLD"]), float(config["ITSC_NMS_RADIUS"]),
                               float(config["ROAD_NMS_RADIUS"]))
@@ -415,12 +420,13 @@ def infer_one_img(sd: StateDict, spec: ModelSpec, img: np.ndarray, config) -> tu
         if nmax == 0:
             continue
         pad = lambda a: np.pad(a, [(0, nmax - a.shape[0])] + [(0, 0)] * (a.ndim - 1))
-        pts = torch.tensor(np.stack([pad(x[1]) for x in q]))
-        prs = torch.tensor(np.stack([pad(x[2]) for x in q]))
-        val = torch.tensor(np.stack([pad(x[3]) for x in q]))
+        dev = feats[bi].device
+        pts = torch.tensor(np.stack([pad(x[1]) for x in q])).to(dev)
+        prs = torch.tensor(np.stack([pad(x[2]) for x in q])).to(dev)
+        val = torch.tensor(np.stack([pad(x[3]) for x in q])).to(dev)
         with torch.no_grad():
             ts = infer_toponet(sd, spec, feats[bi], pts, prs, val)
-        ts = torch.where(torch.isnan(ts), -100.0, ts).squeeze(-1).numpy()
+        ts = torch.where(torch.isnan(ts), -100.0, ts).squeeze(-1).cpu().numpy()
         for ti in range(len(batch)):
             idx = q[ti][0]
             for si in range(q[ti][1].shape[0]):
@@ -433,4 +439,7 @@ def infer_one_img(sd: StateDict, spec: ModelSpec, img: np.ndarray, config) -> tu
                     edge_cnt[key] += 1.0
     thr = float(config["TOPO_THRESHOLD"])
     edges = [e for e, s in edge_sum.items() if s / edge_cnt[e] > thr]
-    return gp[:, ::-1], np.array(edges).reshape(-1, 2), kp_mask, road_mask
+    out = (gp[:, ::-1], np.array(edges).reshape(-1, 2), kp_mask, road_mask)
+    if return_edge_scores:
+        return out + ({e: s / edge_cnt[e] for e, s in edge_sum.items()},)
+    return out

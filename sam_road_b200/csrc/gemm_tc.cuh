@@ -130,29 +130,52 @@ struct EpiF32 {
     int pos_rows;
     int n_total;
   };
+  // fp32 in/out makes this epilogue HBM-bound for short K (attention proj): one row per lane with
+  // 128 B contiguous per lane and chunk, and the residual of chunk c+1 prefetched into registers
+  // while chunk c is processed, keeps more bytes in flight than the transposed scheme.
   static __device__ __forceinline__ void run(const Params& p, int m0, int M, int n_base, int n_cols,
-                                             const TmemRow& row, float* scratch, int lane) {
-    epi_stream_chunks(n_cols, row, scratch, lane, [&](int c, int rr, int cc, float4 x) {
-      const int n = n_base + c * 32 + cc;
-      const int m = m0 + rr;
-      if (m >= M) return;
-      if (p.bias) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-        x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+                                             const TmemRow& row, float* /*scratch*/, int lane) {
+    const int nchunks = n_cols >> 5;
+    const int m = m0 + lane;
+    const bool valid = m < M;
+    const float* rrow = (p.resid && valid) ? p.resid + static_cast<size_t>(m) * p.ldo + n_base : nullptr;
+    const float* prow = (p.pos && valid)
+                            ? p.pos + static_cast<size_t>(m % p.pos_rows) * p.n_total + n_base
+                            : nullptr;
+    float* orow = p.out + static_cast<size_t>(valid ? m : 0) * p.ldo + n_base;
+    float4 nxt[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) nxt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rrow && nchunks > 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) nxt[i] = reinterpret_cast<const float4*>(rrow)[i];
+    }
+    for (int c = 0; c < nchunks; ++c) {
+      float4 cur[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+      if (rrow && c + 1 < nchunks) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) nxt[i] = reinterpret_cast<const float4*>(rrow + (c + 1) * 32)[i];
       }
-      if (p.pos) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(
-            p.pos + static_cast<size_t>(m % p.pos_rows) * p.n_total + n));
-        x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+      float v[32];
+      row.load(c, v);
+      const int n0 = c * 32;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 x = make_float4(v[4 * i] + cur[i].x, v[4 * i + 1] + cur[i].y, v[4 * i + 2] + cur[i].z,
+                               v[4 * i + 3] + cur[i].w);
+        if (p.bias) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n_base + n0) + i);
+          x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+        }
+        if (prow) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(prow + n0) + i);
+          x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+        }
+        if (valid) reinterpret_cast<float4*>(orow + n0)[i] = x;
       }
-      float* o = p.out + static_cast<size_t>(m) * p.ldo + n;
-      if (p.resid) {
-        const float4 b =
-            *reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(m) * p.ldo + n);
-        x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
-      }
-      *reinterpret_cast<float4*>(o) = x;
-    });
+    }
   }
 };
 
