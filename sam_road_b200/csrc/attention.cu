@@ -255,9 +255,11 @@ static int launch_attention_tc(const __half* qkv, const float* qkv_bias, const _
   AtcParams p;
   p.qkv_bias = qkv_bias; p.out = out; p.B = B; p.s = s; p.heads = heads; p.D = D;
   p.nwin = kWindow ? (s + WIN - 1) / WIN : 1;
-  p.scale = 0.125f;
+  p.scale_log2e = 0.125f * 1.4426950408889634f;
   const int units = kWindow ? B * p.nwin * p.nwin * heads : B * (T / 256) * heads;
-  kern<<<units, kAtcThreads, kAtcSmemBytes, st>>>(tmQKV, tmTab, p);
+  p.num_units = units;
+  const int grid = units < device_sm_count() ? units : device_sm_count();   // persistent CTAs
+  kern<<<grid, kAtcThreads, kAtcSmemBytes, st>>>(tmQKV, tmTab, p);
   SRB_CUDA_OK(cudaGetLastError());
   note_launch();
   return 0;

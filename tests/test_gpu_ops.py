@@ -159,13 +159,14 @@ def test_encoder_attention(B, s, win, heads, hd):
     torch.cuda.synchronize()
     diff = (out.float().view(B, s, s, D) - ref).abs()
     err = diff.max().item()
-    if not err < 3e-3:   # diagnostics: where is it wrong?
+    tol = 1.5e-3 * max(1.0, ref.abs().max().item())   # fp16 P / output rounding: a few output ulps
+    if not err < tol:   # diagnostics: where is it wrong?
         per_head = diff.view(B, s, s, heads, hd).amax(dim=(0, 1, 2, 4)).tolist()
         per_y = diff.amax(dim=(0, 2, 3)).tolist()
         per_x = diff.amax(dim=(0, 1, 3)).tolist()
         nan = int(torch.isnan(out.float()).sum().item())
         print(f"attention mismatch: max {err} nan {nan}\n per_head {per_head}\n per_y {per_y}\n per_x {per_x}")
-    assert err < 3e-3, err
+    assert err < tol, (err, tol)
 
 
 @pytest.mark.parametrize("B,s,win", [(3, 32, 14), (3, 32, 32), (5, 16, 14), (5, 16, 16)])
