@@ -249,7 +249,7 @@ static int launch_attention_tc(const __half* qkv, const float* qkv_bias, const _
   static bool attr_set = false;
   if (!attr_set) {
     SRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     kAtcSmemBytes));
+                                     AtcSmem<kWindow>::kBytes));
     attr_set = true;
   }
   AtcParams p;
@@ -259,7 +259,7 @@ static int launch_attention_tc(const __half* qkv, const float* qkv_bias, const _
   const int units = kWindow ? B * p.nwin * p.nwin * heads : B * (T / 256) * heads;
   p.num_units = units;
   const int grid = units < device_sm_count() ? units : device_sm_count();   // persistent CTAs
-  kern<<<grid, kAtcThreads, kAtcSmemBytes, st>>>(tmQKV, tmTab, p);
+  kern<<<grid, kAtcThreads, AtcSmem<kWindow>::kBytes, st>>>(tmQKV, tmTab, p);
   SRB_CUDA_OK(cudaGetLastError());
   note_launch();
   return 0;

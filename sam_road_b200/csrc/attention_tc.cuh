@@ -36,15 +36,23 @@
 namespace srb {
 
 constexpr int kAtcThreads = 384;
-constexpr int kAtcKVStages = 3;
 
 // shared memory map (bytes from a 1024-aligned base)
-constexpr int kAtcOffQ = 0;                       // 256 rows x 128 B
-constexpr int kAtcOffTab = 32768;                 // <=128 rows x 128 B
-constexpr int kAtcOffKV = 49152;                  // global: 3 x (K 16K + V 16K); window: K 32K + V 32K
-constexpr int kAtcOffP = kAtcOffKV + 98304;       // 2 groups x 2 k-blocks x 16 KB (also gather scratch)
-constexpr int kAtcOffBar = kAtcOffP + 65536;
-constexpr int kAtcSmemBytes = kAtcOffBar + 512 + 1024;
+//   global: Q 32 KB | Tab 16 KB | K/V ring 3 x (16 K + 16 K) | P 64 KB
+//   window: Q 32 KB | Tab 16 KB | K/V 2 x (K 208 rows + V 208 rows) double-buffered across units | P 64 KB
+template <bool kWindow>
+struct AtcSmem {
+  static constexpr int kQStages = 1;
+  static constexpr int kKVStages = kWindow ? 2 : 3;
+  static constexpr int kOffQ = 0;
+  static constexpr int kOffTab = kQStages * 32768;
+  static constexpr int kOffKV = kOffTab + 16384;
+  static constexpr int kKVHalf = kWindow ? 208 * 128 : 16384;     // bytes of the K (or V) part of a stage
+  static constexpr int kKVStage = 2 * kKVHalf;
+  static constexpr int kOffP = kOffKV + kKVStages * kKVStage;   // 2 groups x 2 k-blocks x 16 KB
+  static constexpr int kOffBar = kOffP + 65536;
+  static constexpr int kBytes = kOffBar + 512 + 1024;
+};
 
 struct AtcParams {
   const float* qkv_bias;   // [3D] fp32
@@ -102,23 +110,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint8_t* sQ = smem + kAtcOffQ;
-  uint8_t* sTab = smem + kAtcOffTab;
-  uint8_t* sKV = smem + kAtcOffKV;
-  uint8_t* sP = smem + kAtcOffP;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kAtcOffBar);
+  using SM = AtcSmem<kWindow>;
+  constexpr int QST = SM::kQStages;
+  constexpr int kAtcKVStages = SM::kKVStages;
+  constexpr int KVH = SM::kKVHalf;
+  uint8_t* sQ = smem + SM::kOffQ;
+  uint8_t* sTab = smem + SM::kOffTab;
+  uint8_t* sKV = smem + SM::kOffKV;
+  uint8_t* sP = smem + SM::kOffP;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::kOffBar);
   uint64_t* tab_full = bars + 0;
-  uint64_t* q_full = bars + 1;
-  uint64_t* q_empty = bars + 2;
-  uint64_t* t_ready = bars + 3;
-  uint64_t* kv_fixed = bars + 4;
-  uint64_t* kv_full = bars + 5;                 // [kAtcKVStages]
-  uint64_t* kv_empty = bars + 8;                // [kAtcKVStages]
-  uint64_t* s_ready = bars + 11;                // [2]
-  uint64_t* s_free = bars + 13;                 // [2]
-  uint64_t* p_ready = bars + 15;                // [2]
-  uint64_t* pv_done = bars + 17;                // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  uint64_t* t_ready = bars + 1;
+  uint64_t* kv_fixed = bars + 2;
+  uint64_t* q_full = bars + 3;                  // [2]
+  uint64_t* q_empty = bars + 5;                 // [2]
+  uint64_t* kv_full = bars + 7;                 // [<=3]
+  uint64_t* kv_empty = bars + 10;               // [<=3]
+  uint64_t* s_ready = bars + 13;                // [2]
+  uint64_t* s_free = bars + 15;                 // [2]
+  uint64_t* p_ready = bars + 17;                // [2]
+  uint64_t* pv_done = bars + 19;                // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -128,8 +140,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmTab);
     mbar_init(tab_full, 1);
-    mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
     mbar_init(t_ready, 1);
     mbar_init(kv_fixed, 256);
     for (int i = 0; i < kAtcKVStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
@@ -145,11 +156,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
   if constexpr (kWindow) {
     // rows >= 196 of the Q/K/V tiles are never written by TMA: zero them once (V rows must be
     // finite because P = 0 there; Q/K rows only feed masked / unstored entries)
-    for (int i = threadIdx.x; i < (256 - KEYS) * 8; i += kAtcThreads) {
-      const int off = KEYS * 128 + i * 16;
-      *reinterpret_cast<uint4*>(sQ + off) = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < (256 - KEYS) * 8; i += kAtcThreads)
+      *reinterpret_cast<uint4*>(sQ + KEYS * 128 + i * 16) = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < (208 - KEYS) * 8 * 2 * kAtcKVStages; i += kAtcThreads) {
+      const int part = i / ((208 - KEYS) * 8);          // (stage, K|V)
+      const int off = part * KVH + KEYS * 128 + (i % ((208 - KEYS) * 8)) * 16;
       *reinterpret_cast<uint4*>(sKV + off) = make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(sKV + 32768 + off) = make_uint4(0, 0, 0, 0);
     }
     fence_proxy_async_smem();
   }
@@ -170,23 +182,30 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       for (int u = blockIdx.x; u < p.num_units; u += gridDim.x, ++ui) {
         const AtcUnit un = atc_decode<kWindow, WIN>(u, p);
         const int colQ = un.head * 64, colK = p.D + un.head * 64, colV = 2 * p.D + un.head * 64;
-        mbar_wait(q_empty, (ui & 1) ^ 1u);
+        const int qs = ui % QST;
+        const uint32_t qpar = static_cast<uint32_t>((ui / QST) & 1);
+        uint8_t* qdst = sQ + qs * 32768;
         if constexpr (kWindow) {
-          mbar_arrive_expect_tx(q_full, KEYS * 128);
-          tma_load_4d(sQ, &tmQKV, q_full, colQ, un.wx * WIN, un.wy * WIN, un.b);
-          mbar_wait(&kv_empty[0], (ui & 1) ^ 1u);
-          mbar_arrive_expect_tx(&kv_full[0], 2 * KEYS * 128);
-          tma_load_4d(sKV, &tmQKV, &kv_full[0], colK, un.wx * WIN, un.wy * WIN, un.b);
-          tma_load_4d(sKV + 32768, &tmQKV, &kv_full[0], colV, un.wx * WIN, un.wy * WIN, un.b);
+          // K/V of the next unit first (longest chain: TMA -> pad fix-up -> first QK^T)
+          const int ks = ui % kAtcKVStages;
+          mbar_wait(&kv_empty[ks], (((ui / kAtcKVStages) & 1) ^ 1u));
+          mbar_arrive_expect_tx(&kv_full[ks], 2 * KEYS * 128);
+          tma_load_4d(sKV + ks * SM::kKVStage, &tmQKV, &kv_full[ks], colK, un.wx * WIN, un.wy * WIN, un.b);
+          tma_load_4d(sKV + ks * SM::kKVStage + KVH, &tmQKV, &kv_full[ks], colV, un.wx * WIN,
+                      un.wy * WIN, un.b);
+          mbar_wait(&q_empty[qs], qpar ^ 1u);
+          mbar_arrive_expect_tx(&q_full[qs], KEYS * 128);
+          tma_load_4d(qdst, &tmQKV, &q_full[qs], colQ, un.wx * WIN, un.wy * WIN, un.b);
         } else {
           const int row0 = un.b * T;
-          mbar_arrive_expect_tx(q_full, 256 * 128);
-          tma_load_2d(sQ, &tmQKV, q_full, colQ, row0 + un.slab * 256);
-          tma_load_2d(sQ + 16384, &tmQKV, q_full, colQ, row0 + un.slab * 256 + 128);
+          mbar_wait(&q_empty[qs], qpar ^ 1u);
+          mbar_arrive_expect_tx(&q_full[qs], 256 * 128);
+          tma_load_2d(qdst, &tmQKV, &q_full[qs], colQ, row0 + un.slab * 256);
+          tma_load_2d(qdst + 16384, &tmQKV, &q_full[qs], colQ, row0 + un.slab * 256 + 128);
           for (int jb = 0; jb < NBLK; ++jb, ++gb) {
             const int stage = gb % kAtcKVStages;
             mbar_wait(&kv_empty[stage], ((gb / kAtcKVStages) & 1) ^ 1u);
-            uint8_t* dst = sKV + stage * 32768;
+            uint8_t* dst = sKV + stage * SM::kKVStage;
             mbar_arrive_expect_tx(&kv_full[stage], 32768);
             tma_load_2d(dst, &tmQKV, &kv_full[stage], colK, row0 + jb * 128);
             tma_load_2d(dst + 16384, &tmQKV, &kv_full[stage], colV, row0 + jb * 128);
@@ -202,7 +221,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       for (int u = blockIdx.x; u < p.num_units; u += gridDim.x, ++ui) {
         const AtcUnit un = atc_decode<kWindow, WIN>(u, p);
         const int nact = atc_group1_active<kWindow, WIN>(un, p) ? 2 : 1;
-        mbar_wait(q_full, ui & 1);
+        const int qs = ui % QST;
+        const uint8_t* sQu = sQ + qs * 32768;
+        const int ks = ui % kAtcKVStages;                  // window mode: K/V stage of this unit
+        mbar_wait(&q_full[qs], (ui / QST) & 1);
         tc_fence_after_sync();
         {   // rel-pos projections T_g = Q_g * Tab^T into the S regions
           constexpr uint32_t idT = umma_idesc_f16(128, NTAB);
@@ -212,7 +234,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
               mbar_wait(&s_free[g], (wcnt[g] - 1) & 1);
               tc_fence_after_sync();
             }
-            const uint64_t adesc = umma_desc_k128(smem_u32(sQ + g * 16384));
+            const uint64_t adesc = umma_desc_k128(smem_u32(sQu + g * 16384));
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_f16_ss(tmem_base + g * 128, adesc + 2 * k, bdesc + 2 * k, idT, k != 0 ? 1u : 0u);
@@ -236,8 +258,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
               const int jb = npv[g];
               const int nkeys = (kWindow && jb == NBLK - 1) ? kLastMma : 128;
               const uint32_t pbase = smem_u32(sP + g * 32768);
-              const uint32_t vbase = kWindow ? smem_u32(sKV + 32768 + jb * 16384)
-                                             : smem_u32(sKV + ((gb0 + jb) % kAtcKVStages) * 32768 + 16384);
+              const uint32_t vbase = kWindow ? smem_u32(sKV + ks * SM::kKVStage + KVH + jb * 16384)
+                                             : smem_u32(sKV + ((gb0 + jb) % kAtcKVStages) * SM::kKVStage + KVH);
               constexpr uint32_t idPV = umma_idesc_f16_bmn(128, 64);
               const uint32_t d = tmem_base + 256 + g * 64;
               for (int k = 0; k < nkeys / 16; ++k) {
@@ -261,7 +283,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
               bool ok = mbar_try_wait(&s_free[g], (wcnt[g] - 1) & 1);
               if (ok && jb >= kv_seen) {
                 if (kWindow) {
-                  if (jb == 0 && !mbar_try_wait(&kv_full[0], ui & 1)) ok = false;
+                  if (jb == 0 && !mbar_try_wait(&kv_full[ks], (ui / kAtcKVStages) & 1)) ok = false;
                   else kv_seen = NBLK;            // one TMA filled the whole window
                 } else {
                   const int gbk = gb0 + jb;
@@ -272,10 +294,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
               if (ok) {
                 tc_fence_after_sync();
                 const int nkeys = (kWindow && jb == NBLK - 1) ? kLastMma : 128;
-                const uint32_t kbase = kWindow ? smem_u32(sKV + jb * 16384)
-                                               : smem_u32(sKV + ((gb0 + jb) % kAtcKVStages) * 32768);
+                const uint32_t kbase = kWindow ? smem_u32(sKV + ks * SM::kKVStage + jb * 16384)
+                                               : smem_u32(sKV + ((gb0 + jb) % kAtcKVStages) * SM::kKVStage);
                 const uint32_t idS = umma_idesc_f16(128, nkeys);
-                const uint64_t adesc = umma_desc_k128(smem_u32(sQ + g * 16384));
+                const uint64_t adesc = umma_desc_k128(smem_u32(sQu + g * 16384));
                 const uint64_t bdesc = umma_desc_k128(kbase);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
@@ -287,11 +309,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             }
           }
           if (!q_released && ns[0] == NBLK && (nact == 1 || ns[1] == NBLK)) {
-            umma_commit(q_empty);               // Q tile may be overwritten once these MMAs retire
+            umma_commit(&q_empty[qs]);          // Q tile may be overwritten once these MMAs retire
             q_released = true;
           }
         }
-        if constexpr (kWindow) umma_commit(&kv_empty[0]);
+        if constexpr (kWindow) umma_commit(&kv_empty[ks]);
         for (int g = 0; g < nact; ++g) bcnt[g] += NBLK;
       }
     }
@@ -324,8 +346,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         q_real = qrow < KEYS && qy < ry && qx < rx;
         out_tok = static_cast<size_t>(un.b) * T + (un.wy * WIN + qy) * p.s + (un.wx * WIN + qx);
         // pad tokens of the window: k = b_k, v = b_v (fp16) written into the swizzled tiles once the
-        // K/V TMA has landed (it zero-fills them); then hand the tiles to the MMA warp
-        mbar_wait(&kv_full[0], ui & 1);
+        // K/V TMA has landed (it zero-fills them); then hand the tiles to the MMA warp.
+        // t_ready(ui) first: it is committed by the MMA warp inside unit ui, so no thread (in
+        // particular none of an inactive group 1, which has nothing else to wait for) can arrive on
+        // kv_fixed for a later unit before the MMA warp has consumed this unit's phase.
+        mbar_wait(t_ready, ui & 1);
+        const int ks = ui % kAtcKVStages;
+        uint8_t* kvs = sKV + ks * SM::kKVStage;
+        mbar_wait(&kv_full[ks], (ui / kAtcKVStages) & 1);
         const int r = (warp - 4) * 32 + lane;      // 0..255 : one key row per thread
         if (r < KEYS && (r / WIN >= ry || r % WIN >= rx)) {
           const float* bk = p.qkv_bias + p.D + un.head * 64;
@@ -342,8 +370,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             uv.z = pack_half2(__ldg(bv + c * 8 + 4), __ldg(bv + c * 8 + 5));
             uv.w = pack_half2(__ldg(bv + c * 8 + 6), __ldg(bv + c * 8 + 7));
             const int off = r * 128 + ((c ^ (r & 7)) << 4);
-            *reinterpret_cast<uint4*>(sKV + off) = uk;
-            *reinterpret_cast<uint4*>(sKV + 32768 + off) = uv;
+            *reinterpret_cast<uint4*>(kvs + off) = uk;
+            *reinterpret_cast<uint4*>(kvs + KVH + off) = uv;
           }
         }
         fence_proxy_async_smem();
@@ -361,7 +389,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       // rel_h[kh] = T_h[qy - kh + WIN-1] ; rel_w[kw] = T_w[qx - kw + WIN-1]  (image_encoder.py:318-322)
       float rel_h[WIN], rel_w[WIN];
       {
-        mbar_wait(t_ready, ui & 1);
+        if constexpr (!kWindow) mbar_wait(t_ready, ui & 1);
         tc_fence_after_sync();
         const int sy = (kWindow && qrow >= KEYS) ? 0 : qy;
         const int sx = (kWindow && qrow >= KEYS) ? 0 : qx;
@@ -414,16 +442,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             if constexpr (!kWindow) {
               // keys of chunk c of block jb: kh = jb*(128/WIN) + (c*32+i)/WIN, kw = (c*32+i) % WIN
               constexpr int NU = (32 + WIN - 1) / WIN;   // key rows spanned by a 32-key chunk (1 or 2)
-              float mc[NU];
+              float mc[NU], mq[NU][4];
 #pragma unroll
-              for (int uu = 0; uu < NU; ++uu) mc[uu] = -INFINITY;
+              for (int uu = 0; uu < NU; ++uu)
+                mq[uu][0] = mq[uu][1] = mq[uu][2] = mq[uu][3] = -INFINITY;
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
                 const float v = fmaf(__uint_as_float(sraw[c * 32 + i]), p.scale_log2e,
                                      rel_w[(c * 32 + i) % WIN]);
                 y[c * 32 + i] = v;
-                mc[i / WIN] = fmaxf(mc[i / WIN], v);
+                mq[i / WIN][i & 3] = fmaxf(mq[i / WIN][i & 3], v);
               }
+#pragma unroll
+              for (int uu = 0; uu < NU; ++uu)
+                mc[uu] = fmaxf(fmaxf(mq[uu][0], mq[uu][1]), fmaxf(mq[uu][2], mq[uu][3]));
               float best = -INFINITY;
 #pragma unroll
               for (int uu = 0; uu < NU; ++uu) {
@@ -439,6 +471,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
               m_blk = fmaxf(m_blk, best);
             } else {
 #pragma unroll
+              float mq[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
               for (int i = 0; i < 32; ++i) {
                 const int key = jb * 128 + c * 32 + i;
                 float v = -INFINITY;
@@ -446,19 +480,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
                   v = fmaf(__uint_as_float(sraw[c * 32 + i]), p.scale_log2e,
                            rel_h[key / WIN] + rel_w[key % WIN]);
                 y[c * 32 + i] = v;
-                m_blk = fmaxf(m_blk, v);
+                mq[i & 3] = fmaxf(mq[i & 3], v);
               }
+              m_blk = fmaxf(m_blk, fmaxf(fmaxf(mq[0], mq[1]), fmaxf(mq[2], mq[3])));
             }
           }
         }
         // ---- lazy reference max: rescale O / l only when the row max grew by more than 2^8 ----
+        bool pv_waited = false;
         if (jb == 0) {
           m_ref = m_blk;
         } else {
-          mbar_wait(&pv_done[g], par ^ 1u);        // PV(jb-1) retired: P buffer free, O readable
-          tc_fence_after_sync();
           const bool grow = m_blk > m_ref + 8.0f;
           if (__any_sync(0xffffffffu, grow)) {
+            mbar_wait(&pv_done[g], par ^ 1u);      // PV(jb-1) retired: O may be read-modified
+            tc_fence_after_sync();
+            pv_waited = true;
             const float m_new = grow ? m_blk : m_ref;
             const float alpha = ex2_approx(m_ref - m_new);
             m_ref = m_new;
@@ -474,32 +511,44 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             tmem_st_wait();
           }
         }
-        // ---- p = 2^(y - m_ref), row sum, P -> smem (fp16, swizzled) ----
-        float lsum = 0.f;
+        // ---- p = 2^(y - m_ref) packed to fp16 in registers, row sum (4 partial sums) ----
+        uint32_t pk[64];
+        float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           if (c < nchunk) {
             const float sub = rhc[c] - m_ref;
-            float pv[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              pv[i] = ex2_approx(y[c * 32 + i] + sub);
-              lsum += pv[i];
+            for (int i = 0; i < 32; i += 4) {
+              const float p0 = ex2_approx(y[c * 32 + i + 0] + sub);
+              const float p1 = ex2_approx(y[c * 32 + i + 1] + sub);
+              const float p2 = ex2_approx(y[c * 32 + i + 2] + sub);
+              const float p3 = ex2_approx(y[c * 32 + i + 3] + sub);
+              ls0 += p0; ls1 += p1; ls2 += p2; ls3 += p3;
+              pk[c * 16 + i / 2] = pack_half2(p0, p1);
+              pk[c * 16 + i / 2 + 1] = pack_half2(p2, p3);
             }
+          }
+        }
+        l_run += (ls0 + ls1) + (ls2 + ls3);
+        // ---- P -> smem (swizzled) once PV(jb-1) has finished reading the buffer ----
+        if (jb > 0 && !pv_waited) {
+          mbar_wait(&pv_done[g], par ^ 1u);
+          tc_fence_after_sync();
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c < nchunk) {
             uint8_t* dst = myP + (c >> 1) * 16384;
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
-              uint4 uo;
-              uo.x = pack_half2(pv[q4 * 8 + 0], pv[q4 * 8 + 1]);
-              uo.y = pack_half2(pv[q4 * 8 + 2], pv[q4 * 8 + 3]);
-              uo.z = pack_half2(pv[q4 * 8 + 4], pv[q4 * 8 + 5]);
-              uo.w = pack_half2(pv[q4 * 8 + 6], pv[q4 * 8 + 7]);
+              const uint4 uo = make_uint4(pk[c * 16 + q4 * 4 + 0], pk[c * 16 + q4 * 4 + 1],
+                                          pk[c * 16 + q4 * 4 + 2], pk[c * 16 + q4 * 4 + 3]);
               const int piece = (c & 1) * 4 + q4;
               *reinterpret_cast<uint4*>(dst + ((piece ^ sw) << 4)) = uo;
             }
           }
         }
-        l_run += lsum;
         tc_fence_before_sync();
         fence_proxy_async_smem();
         mbar_arrive(&p_ready[g]);
