@@ -301,6 +301,10 @@ __device__ __forceinline__ void tmem_ld_wait() {
 int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                      uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols = 64);
 
+// 2D fp32 row-major tensor, box [box_rows][32 cols] (= 128 B inner), 128B swizzle.
+int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                     uint64_t ld_elems, uint32_t box_rows);
+
 // 4D fp16 view [d3][d2][d1][d0] (d0 contiguous; strides in elements for d1..d3), box {b0,b1,b2,b3},
 // 128B swizzle (b0 * 2 bytes must be 128).  Out-of-bounds elements read as zero.
 int make_tmap_f16_4d(CUtensorMap* out, const void* base, const uint64_t dims[4],

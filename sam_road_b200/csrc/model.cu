@@ -118,6 +118,7 @@ struct samroad_ctx {
   __half* tp_feat_w = nullptr; float* tp_feat_b = nullptr;
   __half* tp_st_w = nullptr; float* tp_off_w = nullptr; float* tp_pair_b = nullptr;
   TopoLayerW tp_layers[3];
+  __half* tp_chunks = nullptr;   // fused-kernel weight chunks [18*128, 128]
   float* tp_out_w = nullptr; float* tp_out_b = nullptr;
 
   // activation workspace (grown on demand)
@@ -577,6 +578,25 @@ extern "C" int samroad_finalize_weights(samroad_handle_t h) {
       t.n2_b = P.f32(K("norm2.bias"), {128});
     }
   }
+  if (c.toponet_version != SAMROAD_TOPO_NO_TRANSFORMER && P.ok) {
+    // fused-kernel operand: per layer Wq, Wk, Wv (= in_proj rows), Wo, W1, W2 as [128,128] chunks
+    std::vector<__half> chunks(static_cast<size_t>(18) * 128 * 128);
+    for (int l = 0; l < 3; ++l) {
+      auto K = [&](const char* suffix) {
+        return fmt_key("topo_net.transformer_encoder.layers.%d.", l) + suffix;
+      };
+      const HostTensor* src[4] = {P.get(K("self_attn.in_proj_weight"), {384, 128}),
+                                  P.get(K("self_attn.out_proj.weight"), {128, 128}),
+                                  P.get(K("linear1.weight"), {128, 128}),
+                                  P.get(K("linear2.weight"), {128, 128})};
+      size_t off = static_cast<size_t>(l) * 6 * 128 * 128;
+      for (int t = 0; t < 4 && P.ok; ++t) {
+        for (size_t i = 0; i < src[t]->data.size(); ++i) chunks[off + i] = __float2half_rn(src[t]->data[i]);
+        off += src[t]->data.size();
+      }
+    }
+    h->tp_chunks = P.upload(chunks);
+  }
   h->tp_out_w = P.f32("topo_net.output_proj.weight", {1, 128});
   h->tp_out_b = P.f32("topo_net.output_proj.bias", {1});
 
@@ -748,6 +768,21 @@ extern "C" int samroad_toponet(samroad_handle_t h, const float* image_embeddings
   SRB_T(KT_TOPO_PAIR, tokd * 128 * 6, tokd * 128 * (8 + 6),
         topo_pair_features(w.PST, h->tp_off_w, h->tp_pair_b, points, pts_dtype, pairs, pairs_dtype, B,
                            N, Ns, Np, zero_off, w.X32, w.X16, st));
+  if (!no_tf && Np == 16) {
+    // all three encoder layers + output_proj in one persistent tcgen05 kernel
+    TopoFusedParams fp;
+    for (int l = 0; l < 3; ++l) {
+      const TopoLayerW& t = h->tp_layers[l];
+      fp.in_b[l] = t.in_b; fp.out_b[l] = t.out_b; fp.l1_b[l] = t.l1_b; fp.l2_b[l] = t.l2_b;
+      fp.n1_g[l] = t.n1_g; fp.n1_b[l] = t.n1_b; fp.n2_g[l] = t.n2_g; fp.n2_b[l] = t.n2_b;
+    }
+    fp.out_w = h->tp_out_w; fp.out_b_final = h->tp_out_b;
+    SRB_T(KT_TOPO_GEMM, tokd * 2 * 128 * (384 + 128 * 3) * 3 + tokd * 4 * 16 * 128 * 3,
+          tokd * 128 * 6 + tokd * 8,
+          topo_transformer_fused(w.X32, w.X16, h->tp_chunks, fp, w.VF, tok, topo_logits, topo_scores,
+                                 st));
+    return 0;
+  }
   if (!no_tf) {
     for (int l = 0; l < 3; ++l) {
       const TopoLayerW& t = h->tp_layers[l];

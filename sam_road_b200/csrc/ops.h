@@ -72,6 +72,16 @@ int topo_attention(const __half* qkv, const uint8_t* valid, int rows, int Np, __
 int topo_output(const float* x32, const uint8_t* valid_fixed, const float* w, const float* b,
                 int tokens, float* logits, float* scores, cudaStream_t st);
 
+// fused 3-layer transformer + output_proj for n_pairs == 16 (toponet_tc.cuh)
+struct TopoFusedParams {
+  const float *in_b[3], *out_b[3], *l1_b[3], *l2_b[3], *n1_g[3], *n1_b[3], *n2_g[3], *n2_b[3];
+  const float* out_w;        // [128]
+  const float* out_b_final;  // [1]
+};
+int topo_transformer_fused(const float* x32, const __half* x16, const __half* w_chunks,
+                           const TopoFusedParams& fp, const uint8_t* valid_fixed, int tokens,
+                           float* logits, float* scores, cudaStream_t st);
+
 // ---- mask fusion (kernels.cu) : inferencer.py:79-110 --------------------------------------------------------
 int fuse_masks(const float* scores, int n_tiles, int P, const int* tile_x0, const int* tile_y0,
                int H, int W, uint8_t* keypoint_u8, uint8_t* road_u8, cudaStream_t st);

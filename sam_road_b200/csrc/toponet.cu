@@ -11,6 +11,7 @@
 // keys are excluded from the softmax, and masked slots report output_proj(0) = bias.
 #include "common.cuh"
 #include "ops.h"
+#include "toponet_tc.cuh"
 
 namespace srb {
 
@@ -234,6 +235,41 @@ int topo_output(const float* x32, const uint8_t* valid_fixed, const float* w, co
   if (tokens <= 0) return 0;
   topo_output_kernel<<<(tokens + 7) / 8, 256, 0, st>>>(x32, valid_fixed, w, b, tokens, logits,
                                                        scores);
+  SRB_CUDA_OK(cudaGetLastError());
+  note_launch();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused transformer launcher (n_pairs == 16): x32/x16 [tokens,128] from topo_pair_features,
+// weights = 18 chunks [128x128] fp16 in consumption order (per layer: Wq, Wk, Wv, Wo, W1, W2)
+// ------------------------------------------------------------------------------------------------
+int topo_transformer_fused(const float* x32, const __half* x16, const __half* w_chunks,
+                           const TopoFusedParams& fp, const uint8_t* valid_fixed, int tokens,
+                           float* logits, float* scores, cudaStream_t st) {
+  if (tokens <= 0) return 0;
+  CUtensorMap tmX16, tmX32, tmW;
+  if (int rc = make_tmap_f16_2d(&tmX16, x16, tokens, 128, 128, 128)) return rc;
+  if (int rc = make_tmap_f32_2d(&tmX32, x32, tokens, 128, 128, 128)) return rc;
+  if (int rc = make_tmap_f16_2d(&tmW, w_chunks, 18 * 128, 128, 128, 128)) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SRB_CUDA_OK(cudaFuncSetAttribute(toponet_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kTtcSmemBytes));
+    attr_set = true;
+  }
+  TtcParams p;
+  for (int l = 0; l < 3; ++l) {
+    p.layer[l].in_b = fp.in_b[l]; p.layer[l].out_b = fp.out_b[l];
+    p.layer[l].l1_b = fp.l1_b[l]; p.layer[l].l2_b = fp.l2_b[l];
+    p.layer[l].n1_g = fp.n1_g[l]; p.layer[l].n1_b = fp.n1_b[l];
+    p.layer[l].n2_g = fp.n2_g[l]; p.layer[l].n2_b = fp.n2_b[l];
+  }
+  p.valid = valid_fixed; p.out_w = fp.out_w; p.out_b = fp.out_b_final;
+  p.logits = logits; p.scores = scores; p.tokens = tokens;
+  p.num_tiles = (tokens + 127) / 128;
+  const int grid = p.num_tiles < device_sm_count() ? p.num_tiles : device_sm_count();
+  toponet_tc_kernel<<<grid, kTtcThreads, kTtcSmemBytes, st>>>(tmX16, tmX32, tmW, p);
   SRB_CUDA_OK(cudaGetLastError());
   note_launch();
   return 0;

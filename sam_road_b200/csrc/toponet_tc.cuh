@@ -1,0 +1,395 @@
+// sam_road_b200 :: fused TopoNet transformer (model.py:74-86,135-146): all three post-norm encoder
+// layers + output_proj for a tile of 128 pair tokens (8 samples x 16 pairs) in ONE persistent kernel.
+//
+// Per layer (torch TransformerEncoderLayer, d=128, 4 heads, ff=128, relu, LN eps 1e-5, eval mode):
+//   qkv = x W_in^T + b_in -> per-sample 16x16 masked attention per head -> x = LN1(x + att W_o^T + b_o)
+//   -> x = LN2(x + relu(x W_1^T + b_1) W_2^T + b_2)
+// The four GEMMs run on tcgen05 (UMMA 128x128x16, fp16 operands, fp32 in TMEM); everything between
+// them stays on chip:
+//   TMEM  cols [0,384)   GEMM accumulators (q|k|v, later out_proj / lin1 / lin2 in [0,128))
+//         cols [384,512) the fp32 residual stream x of the tile (one token per lane)
+//   smem  A buffer 32 KB  current fp16 GEMM A operand (x -> attention output -> x' -> hidden -> x'')
+//         KV buffer 66 KB k and v of the tile as fp16 rows (the x fp32 tile lands here by TMA first)
+//         weight ring 3 x 32 KB  the 18 [128x128] weight chunks streamed by TMA in consumption order
+// Warps: 0 = TMA producer, 1 = MMA issuer + TMEM allocator, 2..5 = the 128 token threads (epilogues,
+// attention on CUDA cores, LayerNorm, output_proj).  Key-padding semantics: masked
+// keys are excluded from the softmax; masked slots report output_proj.bias.
+#pragma once
+
+#include "common.cuh"
+#include "ops.h"
+
+namespace srb {
+
+constexpr int kTtcThreads = 192;
+constexpr int kTtcWStages = 3;
+constexpr int kTtcOffA = 0;                       // 2 k-blocks x 16 KB
+constexpr int kTtcOffKV = 32768;                  // 128 rows x 528 B (k|v fp16, padded) / x fp32 tile
+constexpr int kTtcKVStride = 528;
+constexpr int kTtcOffW = kTtcOffKV + 68608;       // 3 x 32 KB
+constexpr int kTtcOffBar = kTtcOffW + kTtcWStages * 32768;
+constexpr int kTtcSmemBytes = kTtcOffBar + 256 + 1024;
+constexpr int kTtcChunksPerLayer = 6;             // Wq, Wk, Wv, Wo, W1, W2
+
+struct TtcLayerParams {
+  const float* in_b;    // [384]
+  const float* out_b;   // [128]
+  const float* l1_b;    // [128]
+  const float* l2_b;    // [128]
+  const float *n1_g, *n1_b, *n2_g, *n2_b;   // [128]
+};
+
+struct TtcParams {
+  TtcLayerParams layer[3];
+  const uint8_t* valid;   // [tokens] fixed validity (all-invalid rows already flipped), or null
+  const float* out_w;     // [128]
+  const float* out_b;     // [1]
+  float* logits;          // [tokens] or null
+  float* scores;          // [tokens] or null
+  int tokens;
+  int num_tiles;
+};
+
+__device__ __forceinline__ void named_bar_sync_128() {
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kTtcThreads, 1)
+toponet_tc_kernel(const __grid_constant__ CUtensorMap tmX16, const __grid_constant__ CUtensorMap tmX32,
+                  const __grid_constant__ CUtensorMap tmW, TtcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sA = smem + kTtcOffA;
+  uint8_t* sKV = smem + kTtcOffKV;
+  uint8_t* sW = smem + kTtcOffW;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTtcOffBar);
+  uint64_t* x_full = bars + 0;      // TMA: x16 -> A buffer, x32 -> KV buffer
+  uint64_t* a_free = bars + 1;      // MMA commit: last GEMM of the tile retired (A / KV reusable)
+  uint64_t* a_ready = bars + 2;     // 128 token threads: new A operand written
+  uint64_t* acc_ready = bars + 3;   // MMA commit: GEMM result in TMEM
+  uint64_t* w_full = bars + 4;      // [3]
+  uint64_t* w_empty = bars + 7;     // [3]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX16);
+    tma_prefetch_desc(&tmX32);
+    tma_prefetch_desc(&tmW);
+    mbar_init(x_full, 1);
+    mbar_init(a_free, 1);
+    mbar_init(a_ready, 128);
+    mbar_init(acc_ready, 1);
+    for (int i = 0; i < kTtcWStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      int ti = 0, wc = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
+        const int row0 = tile * 128;
+        mbar_wait(a_free, (ti & 1) ^ 1u);
+        mbar_arrive_expect_tx(x_full, 32768 + 65536);
+        tma_load_2d(sA, &tmX16, x_full, 0, row0);
+        tma_load_2d(sA + 16384, &tmX16, x_full, 64, row0);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tma_load_2d(sKV + c * 16384, &tmX32, x_full, c * 32, row0);
+        for (int ch = 0; ch < 3 * kTtcChunksPerLayer; ++ch, ++wc) {
+          const int st = wc % kTtcWStages;
+          mbar_wait(&w_empty[st], ((wc / kTtcWStages) & 1) ^ 1u);
+          mbar_arrive_expect_tx(&w_full[st], 32768);
+          tma_load_2d(sW + st * 32768, &tmW, &w_full[st], 0, ch * 128);
+          tma_load_2d(sW + st * 32768 + 16384, &tmW, &w_full[st], 64, ch * 128);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(128, 128);
+      int ti = 0, wc = 0, ac = 0;   // tiles, weight chunks consumed, a_ready completions consumed
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
+        for (int l = 0; l < 3; ++l) {
+          for (int gemm = 0; gemm < 4; ++gemm) {          // 0: in_proj (3 chunks), 1: out, 2: lin1, 3: lin2
+            // every GEMM overwrites accumulator columns the token threads read in the previous
+            // step, so each one (except the very first) waits for their a_ready arrival; the first
+            // GEMM of a tile additionally waits for the tile's x16 / x32 TMA
+            if (!(ti == 0 && l == 0 && gemm == 0)) {
+              mbar_wait(a_ready, ac & 1);
+              ++ac;
+            }
+            if (l == 0 && gemm == 0) mbar_wait(x_full, ti & 1);
+            tc_fence_after_sync();
+            const int nch = gemm == 0 ? 3 : 1;
+            for (int j = 0; j < nch; ++j, ++wc) {
+              const int st = wc % kTtcWStages;
+              mbar_wait(&w_full[st], (wc / kTtcWStages) & 1);
+              tc_fence_after_sync();
+              const uint32_t abase = smem_u32(sA), wbase = smem_u32(sW + st * 32768);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const uint64_t adesc = umma_desc_k128(abase + (k >> 2) * 16384) + 2 * (k & 3);
+                const uint64_t bdesc = umma_desc_k128(wbase + (k >> 2) * 16384) + 2 * (k & 3);
+                umma_f16_ss(tmem_base + j * 128, adesc, bdesc, idesc, k != 0 ? 1u : 0u);
+              }
+              umma_commit(&w_empty[st]);
+            }
+            umma_commit(acc_ready);
+          }
+        }
+        umma_commit(a_free);
+      }
+    }
+  } else {
+    // =========================== token threads ===========================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t tlane = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t tAcc = tmem_base + tlane;          // cols [0,384)
+    const uint32_t tRes = tmem_base + tlane + 384;    // cols [384,512)
+    const int sw = row & 7;
+    uint8_t* myA = sA + row * 128;
+    int ti = 0, rc = 0;                               // tiles, acc_ready completions consumed
+
+    auto write_a_chunk = [&](int c, const float (&v)[32]) {   // 32 fp32 -> fp16 into the swizzled A buffer
+      uint8_t* dst = myA + (c >> 1) * 16384;
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        uint4 u;
+        u.x = pack_half2(v[q4 * 8 + 0], v[q4 * 8 + 1]);
+        u.y = pack_half2(v[q4 * 8 + 2], v[q4 * 8 + 3]);
+        u.z = pack_half2(v[q4 * 8 + 4], v[q4 * 8 + 5]);
+        u.w = pack_half2(v[q4 * 8 + 6], v[q4 * 8 + 7]);
+        *reinterpret_cast<uint4*>(dst + ((((c & 1) * 4 + q4) ^ sw) << 4)) = u;
+      }
+    };
+    auto ld_chunk = [&](uint32_t taddr, float (&v)[32]) {
+      uint32_t r[32];
+      tmem_ld_32x32(taddr, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    };
+    auto st_chunk = [&](uint32_t taddr, const float (&v)[32]) {
+      uint32_t r[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(v[i]);
+      tmem_st_32x32(taddr, r);
+    };
+    // x = LayerNorm(res + acc + bias) ; res <- x ; optionally A buffer <- fp16(x); returns x.w_out
+    auto residual_layernorm = [&](const float* bias, const float* gamma, const float* beta,
+                                  bool write_a, const float* wdot) -> float {
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float a[32], r[32];
+        ld_chunk(tAcc + c * 32, a);
+        ld_chunk(tRes + c * 32, r);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          r[i] += a[i] + __ldg(bias + c * 32 + i);
+          sum += r[i];
+        }
+        st_chunk(tRes + c * 32, r);
+      }
+      tmem_st_wait();
+      const float mean = sum * (1.0f / 128.0f);
+      float var = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float r[32];
+        ld_chunk(tRes + c * 32, r);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float d = r[i] - mean;
+          var = fmaf(d, d, var);
+        }
+      }
+      const float rstd = rsqrtf(var * (1.0f / 128.0f) + 1e-5f);
+      float dot = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float r[32];
+        ld_chunk(tRes + c * 32, r);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          r[i] = (r[i] - mean) * rstd * __ldg(gamma + c * 32 + i) + __ldg(beta + c * 32 + i);
+          if (wdot) dot = fmaf(r[i], __ldg(wdot + c * 32 + i), dot);
+        }
+        st_chunk(tRes + c * 32, r);
+        if (write_a) write_a_chunk(c, r);
+      }
+      tmem_st_wait();
+      return dot;
+    };
+
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
+      const long tok = static_cast<long>(tile) * 128 + row;
+      const bool tok_ok = tok < p.tokens;
+      // key-validity bits of this token's sample (16 consecutive tokens)
+      uint32_t kmask = 0xffffu;
+      bool my_valid = true;
+      if (p.valid) {
+        kmask = 0;
+        const long s0 = static_cast<long>(tile) * 128 + (row & ~15);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (s0 + j < p.tokens && p.valid[s0 + j]) kmask |= 1u << j;
+        if (kmask == 0) kmask = 0xffffu;            // tail rows beyond `tokens`
+        my_valid = tok_ok && p.valid[tok];
+      }
+
+      // ---- x (fp32) : smem (TMA, 4 boxes of [128 x 32 floats], 128B swizzle) -> TMEM residual ----
+      mbar_wait(x_full, ti & 1);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float v[32];
+        const uint8_t* src = sKV + c * 16384 + row * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 f = *reinterpret_cast<const float4*>(src + ((j ^ sw) << 4));
+          v[4 * j] = f.x; v[4 * j + 1] = f.y; v[4 * j + 2] = f.z; v[4 * j + 3] = f.w;
+        }
+        st_chunk(tRes + c * 32, v);
+      }
+      tmem_st_wait();
+      named_bar_sync_128();                          // every thread is done with the x32 smem tile
+
+      float dot = 0.f;
+#pragma unroll 1
+      for (int l = 0; l < 3; ++l) {
+        const TtcLayerParams& L = p.layer[l];
+        // ================= qkv: k, v -> smem (fp16 rows), attention per head =================
+        mbar_wait(acc_ready, rc & 1); ++rc;
+        tc_fence_after_sync();
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {                 // k: cols 128..255, v: cols 256..383
+          float v[32];
+          ld_chunk(tAcc + 128 + c * 32, v);
+          uint8_t* dst = sKV + row * kTtcKVStride + ((c * 64) ^ (((row >> 4) & 1) << 6));
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint4 u;
+            const float* b = L.in_b + 128 + c * 32 + q4 * 8;
+            u.x = pack_half2(v[q4 * 8 + 0] + __ldg(b + 0), v[q4 * 8 + 1] + __ldg(b + 1));
+            u.y = pack_half2(v[q4 * 8 + 2] + __ldg(b + 2), v[q4 * 8 + 3] + __ldg(b + 3));
+            u.z = pack_half2(v[q4 * 8 + 4] + __ldg(b + 4), v[q4 * 8 + 5] + __ldg(b + 5));
+            u.w = pack_half2(v[q4 * 8 + 6] + __ldg(b + 6), v[q4 * 8 + 7] + __ldg(b + 7));
+            *reinterpret_cast<uint4*>(dst + q4 * 16) = u;
+          }
+        }
+        named_bar_sync_128();
+        const uint8_t* kv0 = sKV + (row & ~15) * kTtcKVStride;   // first token of this sample
+        const int sx = ((row >> 4) & 1) << 6;                    // odd samples: columns XOR 64 B
+#pragma unroll 1
+        for (int h = 0; h < 4; ++h) {
+          float q[32];
+          ld_chunk(tAcc + h * 32, q);
+#pragma unroll
+          for (int i = 0; i < 32; ++i)   // torch MHA scales q by 1/sqrt(head_dim)
+            q[i] = (q[i] + __ldg(L.in_b + h * 32 + i)) * 0.17677669529663687f;
+          float sc[16];
+          float mx = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const uint8_t* kp = kv0 + j * kTtcKVStride + ((h * 64) ^ sx);
+            float acc = 0.f;
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              const uint4 u = *reinterpret_cast<const uint4*>(kp + c4 * 16);
+              const __half2* hh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(hh[e]);
+                acc = fmaf(q[c4 * 8 + 2 * e], f.x, acc);
+                acc = fmaf(q[c4 * 8 + 2 * e + 1], f.y, acc);
+              }
+            }
+            sc[j] = ((kmask >> j) & 1u) ? acc : -INFINITY;
+            mx = fmaxf(mx, sc[j]);
+          }
+          float o[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = 0.f;
+          float lsum = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float pj = __expf(sc[j] - mx);       // exp(-inf) = 0 for masked keys
+            lsum += pj;
+            const uint8_t* vp = kv0 + j * kTtcKVStride + ((256 + h * 64) ^ sx);
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              const uint4 u = *reinterpret_cast<const uint4*>(vp + c4 * 16);
+              const __half2* hh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(hh[e]);
+                o[c4 * 8 + 2 * e] = fmaf(pj, f.x, o[c4 * 8 + 2 * e]);
+                o[c4 * 8 + 2 * e + 1] = fmaf(pj, f.y, o[c4 * 8 + 2 * e + 1]);
+              }
+            }
+          }
+          const float inv = 1.0f / lsum;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] *= inv;
+          write_a_chunk(h, o);                       // attention output columns h*32..h*32+31
+        }
+        tc_fence_before_sync();
+        fence_proxy_async_smem();
+        mbar_arrive(a_ready);
+        // ================= out_proj + residual + LayerNorm1 =================
+        mbar_wait(acc_ready, rc & 1); ++rc;
+        tc_fence_after_sync();
+        residual_layernorm(L.out_b, L.n1_g, L.n1_b, true, nullptr);
+        tc_fence_before_sync();
+        fence_proxy_async_smem();
+        mbar_arrive(a_ready);
+        // ================= linear1 + relu =================
+        mbar_wait(acc_ready, rc & 1); ++rc;
+        tc_fence_after_sync();
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          float v[32];
+          ld_chunk(tAcc + c * 32, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + __ldg(L.l1_b + c * 32 + i), 0.f);
+          write_a_chunk(c, v);
+        }
+        tc_fence_before_sync();
+        fence_proxy_async_smem();
+        mbar_arrive(a_ready);
+        // ================= linear2 + residual + LayerNorm2 =================
+        mbar_wait(acc_ready, rc & 1); ++rc;
+        tc_fence_after_sync();
+        dot = residual_layernorm(L.l2_b, L.n2_g, L.n2_b, l < 2, l == 2 ? p.out_w : nullptr);
+        tc_fence_before_sync();
+        fence_proxy_async_smem();
+        mbar_arrive(a_ready);     // l == 2: releases the accumulator columns for the next tile
+      }
+      // ================= output_proj + sigmoid =================
+      if (tok_ok) {
+        const float b = __ldg(p.out_b);
+        const float lg = my_valid ? dot + b : b;
+        if (p.logits) p.logits[tok] = lg;
+        if (p.scores) p.scores[tok] = 1.0f / (1.0f + expf(-lg));
+      }
+      tc_fence_before_sync();
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace srb
