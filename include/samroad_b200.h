@@ -147,6 +147,9 @@ int samroad_op_attention(const void* qkv16, const float* qkv_bias, const float* 
 /* Test hook: route samroad_op_attention / the encoder through the fp32 SIMT attention kernel (the
  * independent on-device checker of the tcgen05 kernel).  Not for production use. */
 void samroad_debug_force_simt_attention(int on);
+/* Test hook: route every GEMM through the 1-CTA kernels (the 2-CTA cta_group::2 kernel is then
+ * checked against them). */
+void samroad_debug_disable_2cta_gemm(int off);
 
 #ifdef __cplusplus
 }

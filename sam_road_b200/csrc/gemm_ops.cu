@@ -1,11 +1,20 @@
 // sam_road_b200 :: GEMM instantiations and tile-shape dispatch.
 #include "gemm_tc.cuh"
+#include "gemm_tc2.cuh"
 #include "ops.h"
 
 namespace srb {
 
 // 128x256 tiles (4-stage ring, all 512 TMEM columns) when N allows and the grid still fills the GPU,
 // otherwise 128x128 tiles (6-stage ring).
+// 2-CTA 256x256 tiles for the big streaming GEMMs (halves L2->SM operand traffic)
+static bool g_disable_2cta = false;
+void gemm_disable_2cta(bool off) { g_disable_2cta = off; }
+static inline bool use_2cta(int M, int N) {
+  if (g_disable_2cta || N % 256 != 0) return false;
+  return static_cast<long>((M + 255) / 256) * (N / 256) >= device_sm_count() / 2;
+}
+
 static inline bool use_bn256(int M, int N) {
   if (N % 256 != 0) return false;
   const long tiles256 = static_cast<long>((M + kGemmBM - 1) / kGemmBM) * (N / 256);
@@ -16,6 +25,7 @@ int gemm_f16out(const __half* A, int lda, const __half* W, int ldw, int M, int N
                 const float* bias, int act, __half* out, int ldo, cudaStream_t st) {
   EpiF16::Params p{out, bias, ldo, act};
   SRB_REQUIRE(ldo % 8 == 0, "gemm_f16out: ldo=%d must be a multiple of 8", ldo);
+  if (use_2cta(M, N)) return launch_gemm_tc2<EpiF16>(A, lda, W, ldw, M, N, K, p, st);
   if (use_bn256(M, N)) return launch_gemm_tc<256, 4, EpiF16>(A, lda, W, ldw, M, N, K, p, st);
   return launch_gemm_tc<128, 6, EpiF16>(A, lda, W, ldw, M, N, K, p, st);
 }
@@ -25,6 +35,7 @@ int gemm_f32out(const __half* A, int lda, const __half* W, int ldw, int M, int N
                 int ldo, cudaStream_t st) {
   EpiF32::Params p{out, bias, resid, pos, ldo, pos_rows > 0 ? pos_rows : 1, N};
   SRB_REQUIRE(ldo % 4 == 0, "gemm_f32out: ldo=%d must be a multiple of 4", ldo);
+  if (use_2cta(M, N)) return launch_gemm_tc2<EpiF32>(A, lda, W, ldw, M, N, K, p, st);
   if (use_bn256(M, N)) return launch_gemm_tc<256, 4, EpiF32>(A, lda, W, ldw, M, N, K, p, st);
   return launch_gemm_tc<128, 6, EpiF32>(A, lda, W, ldw, M, N, K, p, st);
 }

@@ -1,0 +1,183 @@
+// sam_road_b200 :: 2-CTA tcgen05 GEMM (cta_group::2).  Same contract and epilogues as gemm_tc.cuh, but
+// a cluster of two CTAs (one TPC) computes a 256 x 256 tile with UMMA M = 256: each CTA stages only
+// its 128 rows of A and its 128 rows (N) of W per k-block (32 KB / stage instead of 48 KB for a
+// 128 x 256 tile), halving L2 -> SM operand traffic per FLOP -- the 1-CTA kernel is bound by that
+// traffic (~12.8 TB/s measured, ncu l1tex__m_xbar2l1tex_read_bytes) at ~1.0 PFLOP/s.
+//
+//   both CTAs : warp 0 TMA producer (bytes credited to the leader's full barrier), warps 2..9 epilogue
+//               of their own 128 accumulator rows (TMEM is per SM)
+//   leader    : warp 1 lane 0 issues tcgen05.mma.cta_group::2 and multicasts the commits
+#pragma once
+
+#include "gemm_tc.cuh"
+
+namespace srb {
+
+constexpr int kGemm2Stages = 6;
+
+struct Gemm2Smem {
+  static constexpr int kABytes = 128 * kGemmBK * 2;
+  static constexpr int kStageBytes = 2 * kABytes;                    // A half + B half
+  static constexpr int kBarOffset = kGemm2Stages * kStageBytes;
+  static constexpr int kScratchOffset = kBarOffset + 256;
+  static constexpr int kTotal = kScratchOffset + kGemmEpiWarps * kGemmScratchFloats * 4 + 1024;
+};
+
+template <class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                int M, int N, int K, typename Epi::Params ep) {
+  using SM = Gemm2Smem;
+  constexpr int STAGES = kGemm2Stages;
+  constexpr int BN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  const int num_m = (M + 255) / 256;
+  const int num_n = N / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = (K + kGemmBK - 1) / kGemmBK;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 2);      // leader: arrive.expect_tx + the peer's remote arrive
+      mbar_init(&empty_bar[s], 1);     // multicast commit from the leader's MMA thread
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 2 * (Epi::kSplitCols ? 8 : 4));   // epilogue warps of both CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, 512);
+  tc_fence_before_sync();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + stage * SM::kStageBytes;
+          uint8_t* sb = sa + SM::kABytes;
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * SM::kStageBytes);
+          tma_load_2d_2sm(sa, &tmA, &full_bar[stage], kb * kGemmBK, m_blk * 256 + static_cast<int>(rank) * 128);
+          tma_load_2d_2sm(sb, &tmB, &full_bar[stage], kb * kGemmBK, n_blk * BN + static_cast<int>(rank) * 128);
+          if (!leader) mbar_arrive_remote(&full_bar[stage], 0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(256, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(&tempty_bar[as], aphase ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(smem + stage * SM::kStageBytes);
+          const uint64_t adesc = umma_desc_k128(a_addr);
+          const uint64_t bdesc = umma_desc_k128(a_addr + SM::kABytes);
+#pragma unroll
+          for (int k = 0; k < kGemmBK / 16; ++k)
+            umma_f16_ss_2sm(tmem_d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k),
+                            idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2sm(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_2sm(&tfull_bar[as]);
+        as ^= 1;
+        if (as == 0) aphase ^= 1u;
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..9, both CTAs) =====================
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    if (Epi::kSplitCols || half == 0) {
+      float* scratch = reinterpret_cast<float*>(smem + SM::kScratchOffset) +
+                       (warp - 2) * kGemmScratchFloats;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after_sync();
+        const int m0 = m_blk * 256 + static_cast<int>(rank) * 128 + q * 32;
+        int col0 = 0, n_cols = BN;
+        if (Epi::kSplitCols) { col0 = half * (BN / 2); n_cols = BN / 2; }
+        TmemRow row{tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                    static_cast<uint32_t>(as * BN + col0)};
+        Epi::run(ep, m0, M, n_blk * BN + col0, n_cols, row, scratch, lane);
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_arrive(&tempty_bar[as]);
+          else mbar_arrive_remote(&tempty_bar[as], 0);
+        }
+        as ^= 1;
+        if (as == 0) aphase ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_2sm(tmem_base, 512);
+}
+
+template <class Epi>
+int launch_gemm_tc2(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K,
+                    const typename Epi::Params& ep, cudaStream_t stream) {
+  using SM = Gemm2Smem;
+  SRB_REQUIRE(N % 256 == 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm2: bad shape N=%d K=%d",
+              N, K);
+  CUtensorMap tmA, tmB;
+  if (int rc = make_tmap_f16_2d(&tmA, A, M, K, lda, 128)) return rc;
+  if (int rc = make_tmap_f16_2d(&tmB, W, N, K, ldw, 128)) return rc;
+  auto kern = gemm_tc2_kernel<Epi>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
+    attr_set = true;
+  }
+  const int num_tiles = ((M + 255) / 256) * (N / 256);
+  const int max_clusters = device_sm_count() / 2;
+  const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
+  kern<<<2 * clusters, kGemmThreads, SM::kTotal, stream>>>(tmA, tmB, M, N, K, ep);
+  SRB_CUDA_OK(cudaGetLastError());
+  note_launch(1);
+  return 0;
+}
+
+}  // namespace srb

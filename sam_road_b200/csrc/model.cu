@@ -950,3 +950,4 @@ extern "C" int samroad_op_attention(const void* qkv16, const float* qkv_bias, co
                            static_cast<cudaStream_t>(stream));
 }
 extern "C" void samroad_debug_force_simt_attention(int on) { attention_force_simt(on != 0); }
+extern "C" void samroad_debug_disable_2cta_gemm(int off) { gemm_disable_2cta(off != 0); }

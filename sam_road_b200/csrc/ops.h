@@ -30,6 +30,7 @@ int gemm_dec_final(const __half* A, int lda, const __half* W, int ldw, int M, in
                    const float* bias3, const float* w4, const float* bias4, int s, int P,
                    float* scores, float* logits, cudaStream_t st);
 // plain SIMT fp32-accumulate GEMM used only by the on-device unit tests as an independent checker
+void gemm_disable_2cta(bool off);   // test hook: force the 1-CTA kernels
 int gemm_ref_simt(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K,
                   float* out, int ldo, cudaStream_t st);
 

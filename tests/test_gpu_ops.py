@@ -62,6 +62,27 @@ def test_gemm_f16(M, N, K, act):
         assert (chk + bias - ref).abs().max().item() < 1e-3
 
 
+def test_gemm_2cta_vs_1cta_bitwise():
+    """The cta_group::2 kernel (256x256 cluster tiles) against the 1-CTA kernel: same MMA order per
+    output element, so results must be bit-identical."""
+    lib = _lib.load()
+    M, N, K = 40000, 3072, 768
+    A = _rand16((M, K), 1.0, 21)
+    W = _rand16((N, K), 1.0 / math.sqrt(K), 22)
+    bias = torch.randn(N, device=DEV)
+    outs = []
+    for off in (1, 0):
+        lib.samroad_debug_disable_2cta_gemm(off)
+        out = torch.full((M, N), float("nan"), dtype=torch.float16, device=DEV)
+        _lib.check(lib.samroad_op_gemm_f16(A.data_ptr(), K, W.data_ptr(), K, M, N, K, bias.data_ptr(),
+                                           1, out.data_ptr(), N, _st()), "gemm_f16")
+        torch.cuda.synchronize()
+        outs.append(out)
+    lib.samroad_debug_disable_2cta_gemm(0)
+    assert torch.isfinite(outs[1].float()).all()
+    assert torch.equal(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("M,N,K", [(256, 768, 768), (3000, 768, 3072), (20000, 768, 768), (500, 256, 128)])
 def test_gemm_f32_resid_pos(M, N, K):
     lib = _lib.load()
