@@ -5,8 +5,8 @@
 
 namespace srb {
 
-// 128x256 tiles (4-stage ring, all 512 TMEM columns) when N allows and the grid still fills the GPU,
-// otherwise 128x128 tiles (6-stage ring).
+// 128x256 tiles (3-stage ring, all 512 TMEM columns) when N allows and the grid still fills the GPU,
+// otherwise 128x128 tiles (5-stage ring).
 // 2-CTA 256x256 tiles for the big streaming GEMMs (halves L2->SM operand traffic)
 static bool g_disable_2cta = false;
 void gemm_disable_2cta(bool off) { g_disable_2cta = off; }
@@ -26,8 +26,8 @@ int gemm_f16out(const __half* A, int lda, const __half* W, int ldw, int M, int N
   EpiF16::Params p{out, bias, ldo, act};
   SRB_REQUIRE(ldo % 8 == 0, "gemm_f16out: ldo=%d must be a multiple of 8", ldo);
   if (use_2cta(M, N)) return launch_gemm_tc2<EpiF16>(A, lda, W, ldw, M, N, K, p, st);
-  if (use_bn256(M, N)) return launch_gemm_tc<256, 4, EpiF16>(A, lda, W, ldw, M, N, K, p, st);
-  return launch_gemm_tc<128, 6, EpiF16>(A, lda, W, ldw, M, N, K, p, st);
+  if (use_bn256(M, N)) return launch_gemm_tc<256, 3, EpiF16>(A, lda, W, ldw, M, N, K, p, st);
+  return launch_gemm_tc<128, 5, EpiF16>(A, lda, W, ldw, M, N, K, p, st);
 }
 
 int gemm_f32out(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K,
@@ -36,8 +36,8 @@ int gemm_f32out(const __half* A, int lda, const __half* W, int ldw, int M, int N
   EpiF32::Params p{out, bias, resid, pos, ldo, pos_rows > 0 ? pos_rows : 1, N};
   SRB_REQUIRE(ldo % 4 == 0, "gemm_f32out: ldo=%d must be a multiple of 4", ldo);
   if (use_2cta(M, N)) return launch_gemm_tc2<EpiF32>(A, lda, W, ldw, M, N, K, p, st);
-  if (use_bn256(M, N)) return launch_gemm_tc<256, 4, EpiF32>(A, lda, W, ldw, M, N, K, p, st);
-  return launch_gemm_tc<128, 6, EpiF32>(A, lda, W, ldw, M, N, K, p, st);
+  if (use_bn256(M, N)) return launch_gemm_tc<256, 3, EpiF32>(A, lda, W, ldw, M, N, K, p, st);
+  return launch_gemm_tc<128, 5, EpiF32>(A, lda, W, ldw, M, N, K, p, st);
 }
 
 int gemm_ln(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K,
@@ -49,15 +49,15 @@ int gemm_ln(const __half* A, int lda, const __half* W, int ldw, int M, int N, in
   EpiLN::Params p{out16, out32, out_nchw, bias, resid, gamma, beta, eps, ldo, group, act,
                   tokens > 0 ? tokens : 1, N};
   if (group == 256 || use_bn256(M, N))
-    return launch_gemm_tc<256, 4, EpiLN>(A, lda, W, ldw, M, N, K, p, st);
-  return launch_gemm_tc<128, 6, EpiLN>(A, lda, W, ldw, M, N, K, p, st);
+    return launch_gemm_tc<256, 3, EpiLN>(A, lda, W, ldw, M, N, K, p, st);
+  return launch_gemm_tc<128, 5, EpiLN>(A, lda, W, ldw, M, N, K, p, st);
 }
 
 int gemm_dec_final(const __half* A, int lda, const __half* W, int ldw, int M, int K,
                    const float* bias3, const float* w4, const float* bias4, int s, int P,
                    float* scores, float* logits, cudaStream_t st) {
   EpiDecFinal::Params p{scores, logits, bias3, w4, bias4, s, P};
-  return launch_gemm_tc<128, 6, EpiDecFinal>(A, lda, W, ldw, M, 128, K, p, st);
+  return launch_gemm_tc<128, 5, EpiDecFinal>(A, lda, W, ldw, M, 128, K, p, st);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -35,7 +35,7 @@ constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;
 constexpr int kGemmThreads = 320;
 constexpr int kGemmEpiWarps = 8;
-constexpr int kGemmScratchFloats = 32 * 33;   // per epilogue warp: 32x32 fp32 block, padded rows
+constexpr int kGemmScratchFloats = 32 * 36;   // per epilogue warp: 32x32 fp32 block, rows padded to 36
 
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -59,8 +59,8 @@ struct TmemRow {
 
 // ------------------------------------------------------------------------------------------------
 // Streaming epilogues.  A warp owns 32 tile rows (its TMEM lane quarter) x n_cols columns.  Per
-// 32-column chunk: lane r holds row r's 32 accumulators -> scratch[r][0..31] (row stride 33 floats,
-// conflict-free) -> re-read as "lane l holds columns 4*(l&7).. of row 4*j + (l>>3)", j = 0..7 ->
+// 32-column chunk: lane r holds row r's 32 accumulators -> scratch[r][0..31] (row pitch 36 floats,
+// float4 accesses, conflict-free) -> re-read as "lane l holds columns 4*(l&7).. of row 4*j + (l>>3)", j = 0..7 ->
 // bias / activation / residual in that layout -> 8 lanes cover 128 (fp32) or 64 (fp16) contiguous
 // bytes of a row per store instruction.
 // ------------------------------------------------------------------------------------------------
@@ -72,14 +72,15 @@ __device__ __forceinline__ void epi_stream_chunks(int n_cols, const TmemRow& row
   for (int c = 0; c < nchunks; ++c) {
     float v[32];
     row.load(c, v);
+    // 16-byte accesses with a 36-float row pitch are bank-conflict free in both directions
+    float4* wp = reinterpret_cast<float4*>(scratch + lane * 36);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) scratch[lane * 33 + i] = v[i];
+    for (int i = 0; i < 8; ++i) wp[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int rr = 4 * j + rsub;
-      const float* sp = scratch + rr * 33 + cc;
-      body(c, rr, cc, make_float4(sp[0], sp[1], sp[2], sp[3]));
+      body(c, rr, cc, *reinterpret_cast<const float4*>(scratch + rr * 36 + cc));
     }
     __syncwarp();
   }

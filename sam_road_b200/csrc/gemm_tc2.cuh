@@ -13,7 +13,7 @@
 
 namespace srb {
 
-constexpr int kGemm2Stages = 6;
+constexpr int kGemm2Stages = 5;
 
 struct Gemm2Smem {
   static constexpr int kABytes = 128 * kGemmBK * 2;
