@@ -44,7 +44,7 @@ int gemm_ln(const __half* A, int lda, const __half* W, int ldw, int M, int N, in
             const float* bias, const float* resid, const float* gamma, const float* beta, float eps,
             int group, int act, __half* out16, float* out32, float* out_nchw, int tokens, int ldo,
             cudaStream_t st) {
-  SRB_REQUIRE(group == 128 || group == 256, "gemm_ln: group=%d must be 128 or 256", group);
+  SRB_REQUIRE(group == 64 || group == 128 || group == 256, "gemm_ln: group=%d must be 64, 128 or 256", group);
   SRB_REQUIRE(N % group == 0, "gemm_ln: N=%d not a multiple of group=%d", N, group);
   EpiLN::Params p{out16, out32, out_nchw, bias, resid, gamma, beta, eps, ldo, group, act,
                   tokens > 0 ? tokens : 1, N};

@@ -114,6 +114,9 @@ struct samroad_ctx {
   __half* dec2_w = nullptr; float* dec2_b = nullptr;
   __half* dec3_w = nullptr; float* dec3_b = nullptr;
   float* dec4_w = nullptr; float* dec4_b = nullptr;
+  // SAM mask-decoder path (USE_SAM_DECODER)
+  SamDecoderWeights sam{};
+  void* sam_ws = nullptr; size_t sam_ws_bytes = 0;
   // toponet
   __half* tp_feat_w = nullptr; float* tp_feat_b = nullptr;
   __half* tp_st_w = nullptr; float* tp_off_w = nullptr; float* tp_pair_b = nullptr;
@@ -361,9 +364,6 @@ extern "C" int samroad_create(const SamRoadCfg* cfg, int device, samroad_handle_
   SRB_REQUIRE(hd == 64 || hd == 80, "head_dim=%d unsupported (64 or 80)", hd);
   SRB_REQUIRE(cfg->depth > 0 && cfg->depth <= 64, "depth=%d unsupported", cfg->depth);
   SRB_REQUIRE(cfg->window_size > 0, "window_size=%d must be positive", cfg->window_size);
-  SRB_REQUIRE(cfg->use_sam_decoder == 0,
-              "USE_SAM_DECODER=True (SAM TwoWayTransformer mask decoder) is not built yet in this "
-              "library; only the default naive map_decoder path (model.py:284-295) is available");
   int ndev = 0;
   SRB_CUDA_OK(cudaGetDeviceCount(&ndev));
   SRB_REQUIRE(ndev > 0, "no CUDA device: libsamroad_b200 has no CPU fallback");
@@ -390,6 +390,7 @@ extern "C" int samroad_destroy(samroad_handle_t h) {
   cudaDeviceSynchronize();
   for (void* p : h->weight_allocs) cudaFree(p);
   if (h->ws) cudaFree(h->ws);
+  if (h->sam_ws) cudaFree(h->sam_ws);
   if (h->stage_in) cudaFree(h->stage_in);
   if (h->stage_scores) cudaFree(h->stage_scores);
   if (h->stage_emb) cudaFree(h->stage_emb);
@@ -519,6 +520,7 @@ extern "C" int samroad_finalize_weights(samroad_handle_t h) {
   h->neck3_g = P.f32("image_encoder.neck.3.weight", {256});
   h->neck3_b = P.f32("image_encoder.neck.3.bias", {256});
 
+  if (!c.use_sam_decoder) {
   // ---- naive map decoder (model.py:286-295) ----
   if (const HostTensor* w = P.get("map_decoder.0.weight", {256, 128, 2, 2}))
     h->dec1_w = P.upload(pack_convT(*w, 256, 128));
@@ -539,6 +541,78 @@ extern "C" int samroad_finalize_weights(samroad_handle_t h) {
     h->dec4_w = P.upload(o);
   }
   h->dec4_b = P.f32("map_decoder.7.bias", {2});
+
+  } else {
+    // ---- SAM mask decoder + null-prompt encoder (model.py:260-282) ----
+    SamDecoderWeights& S = h->sam;
+    const std::string md = "mask_decoder.", tr = "mask_decoder.transformer.";
+    if (const HostTensor* it = P.get(md + "iou_token.weight", {1, 256})) {
+      if (const HostTensor* mt = P.get(md + "mask_tokens.weight", {3, 256})) {
+        std::vector<float> tok(it->data);
+        tok.insert(tok.end(), mt->data.begin(), mt->data.end());
+        S.tokens = P.upload(tok);
+      }
+    }
+    S.no_mask_embed = P.f32("prompt_encoder.no_mask_embed.weight", {1, 256});
+    if (const HostTensor* G = P.get("prompt_encoder.pe_layer.positional_encoding_gaussian_matrix", {2, 128})) {
+      // PromptEncoder.get_dense_pe (prompt_encoder.py:62-71,185-205): constant per config
+      std::vector<float> pe(static_cast<size_t>(s) * s * 256);
+      for (int y = 0; y < s; ++y)
+        for (int x = 0; x < s; ++x) {
+          const float cx = 2.0f * ((x + 0.5f) / s) - 1.0f, cy = 2.0f * ((y + 0.5f) / s) - 1.0f;
+          for (int k = 0; k < 128; ++k) {
+            const float a = 6.283185307179586f * (cx * G->data[k] + cy * G->data[128 + k]);
+            pe[(static_cast<size_t>(y) * s + x) * 256 + k] = sinf(a);
+            pe[(static_cast<size_t>(y) * s + x) * 256 + 128 + k] = cosf(a);
+          }
+        }
+      S.dense_pe = P.upload(pe);
+    }
+    auto attn = [&](const std::string& p, int64_t internal) {
+      SamAttnW a;
+      a.qw = P.f32(p + "q_proj.weight", {internal, 256}); a.qb = P.f32(p + "q_proj.bias", {internal});
+      a.kw = P.f32(p + "k_proj.weight", {internal, 256}); a.kb = P.f32(p + "k_proj.bias", {internal});
+      a.vw = P.f32(p + "v_proj.weight", {internal, 256}); a.vb = P.f32(p + "v_proj.bias", {internal});
+      a.ow = P.f32(p + "out_proj.weight", {256, internal}); a.ob = P.f32(p + "out_proj.bias", {256});
+      return a;
+    };
+    for (int l = 0; l < 2; ++l) {
+      const std::string p = tr + "layers." + std::to_string(l) + ".";
+      S.self_attn[l] = attn(p + "self_attn.", 256);
+      S.t2i[l] = attn(p + "cross_attn_token_to_image.", 128);
+      S.i2t[l] = attn(p + "cross_attn_image_to_token.", 128);
+      S.n1g[l] = P.f32(p + "norm1.weight", {256}); S.n1b[l] = P.f32(p + "norm1.bias", {256});
+      S.n2g[l] = P.f32(p + "norm2.weight", {256}); S.n2b[l] = P.f32(p + "norm2.bias", {256});
+      S.n3g[l] = P.f32(p + "norm3.weight", {256}); S.n3b[l] = P.f32(p + "norm3.bias", {256});
+      S.n4g[l] = P.f32(p + "norm4.weight", {256}); S.n4b[l] = P.f32(p + "norm4.bias", {256});
+      S.l1w[l] = P.f32(p + "mlp.lin1.weight", {2048, 256}); S.l1b[l] = P.f32(p + "mlp.lin1.bias", {2048});
+      S.l2w[l] = P.f32(p + "mlp.lin2.weight", {256, 2048}); S.l2b[l] = P.f32(p + "mlp.lin2.bias", {256});
+      S.t2i_kw16[l] = P.linear_w(p + "cross_attn_token_to_image.k_proj.weight", 128, 256);
+      S.t2i_vw16[l] = P.linear_w(p + "cross_attn_token_to_image.v_proj.weight", 128, 256);
+      S.i2t_qw16[l] = P.linear_w(p + "cross_attn_image_to_token.q_proj.weight", 128, 256);
+      S.i2t_ow16[l] = P.linear_w(p + "cross_attn_image_to_token.out_proj.weight", 256, 128);
+    }
+    S.final_attn = attn(tr + "final_attn_token_to_image.", 128);
+    S.t2i_kw16[2] = P.linear_w(tr + "final_attn_token_to_image.k_proj.weight", 128, 256);
+    S.t2i_vw16[2] = P.linear_w(tr + "final_attn_token_to_image.v_proj.weight", 128, 256);
+    S.nfg = P.f32(tr + "norm_final_attn.weight", {256}); S.nfb = P.f32(tr + "norm_final_attn.bias", {256});
+    for (int mi = 0; mi < 2; ++mi)
+      for (int j = 0; j < 3; ++j) {
+        const std::string k = md + "output_hypernetworks_mlps." + std::to_string(mi + 1) + ".layers." +
+                              std::to_string(j) + ".";
+        const int64_t out = j == 2 ? 32 : 256;
+        S.hw[mi][j] = P.f32(k + "weight", {out, 256});
+        S.hb[mi][j] = P.f32(k + "bias", {out});
+      }
+    if (const HostTensor* wt = P.get(md + "output_upscaling.0.weight", {256, 64, 2, 2}))
+      S.up1_w = P.upload(pack_convT(*wt, 256, 64));
+    if (const HostTensor* bt = P.get(md + "output_upscaling.0.bias", {64})) S.up1_b = P.upload(tile4(bt->data));
+    S.up1_g = P.f32(md + "output_upscaling.1.weight", {64});
+    S.up1_beta = P.f32(md + "output_upscaling.1.bias", {64});
+    if (const HostTensor* wt = P.get(md + "output_upscaling.3.weight", {64, 32, 2, 2}))
+      S.up2_w = P.upload(pack_convT(*wt, 64, 32));
+    if (const HostTensor* bt = P.get(md + "output_upscaling.3.bias", {32})) S.up2_b = P.upload(tile4(bt->data));
+  }
 
   // ---- TopoNet (model.py:61-86) ----
   h->tp_feat_w = P.linear_w("topo_net.feature_proj.weight", 128, 256);
@@ -685,7 +759,12 @@ extern "C" int samroad_encode_masks(samroad_handle_t h, const void* rgb, int rgb
                 1e-6f, 256, ACT_NONE, w.FEAT, nullptr, image_embeddings, T, 256, st));
 
   // naive map decoder (model.py:286-295, 490-491) as three GEMMs, pixel shuffle by row indexing
-  if (mask_scores || mask_logits) {
+  if ((mask_scores || mask_logits) && h->cfg.use_sam_decoder) {
+    // SAM mask decoder (model.py:471-488): null prompts, TwoWayTransformer, upscaler, x4 bilinear
+    SRB_TRY(ensure_bytes(&h->sam_ws, &h->sam_ws_bytes, sam_decoder_ws_bytes(B, T)));
+    SRB_T(KT_DECODER, 0.91e9 * B, Md * 256 * 4 * 10,
+          sam_decoder_forward(h->sam, image_embeddings, B, s, P, h->sam_ws, mask_scores, mask_logits, st));
+  } else if (mask_scores || mask_logits) {
     SRB_T(KT_DECODER, 2 * Md * 512 * 256, Md * 256 * 2 + Md * 512 * 2,
           gemm_ln(w.FEAT, 256, h->dec1_w, 256, M, 512, 256, h->dec1_b, nullptr, h->dec_ln_g,
                   h->dec_ln_b, 1e-6f, 128, ACT_GELU, w.D1, nullptr, nullptr, T, 512, st));

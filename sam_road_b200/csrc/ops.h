@@ -83,6 +83,27 @@ int topo_transformer_fused(const float* x32, const __half* x16, const __half* w_
                            const TopoFusedParams& fp, const uint8_t* valid_fixed, int tokens,
                            float* logits, float* scores, cudaStream_t st);
 
+// ---- SAM mask-decoder path (sam_decoder.cu), USE_SAM_DECODER: True --------------------------------
+struct SamAttnW { const float *qw, *qb, *kw, *kb, *vw, *vb, *ow, *ob; };
+struct SamDecoderWeights {
+  const float* tokens;        // [4][256] = [iou_token ; mask_tokens]
+  const float* no_mask_embed; // [256]
+  const float* dense_pe;      // [T][256]
+  SamAttnW self_attn[2], t2i[2], i2t[2], final_attn;
+  const float *n1g[2], *n1b[2], *n2g[2], *n2b[2], *n3g[2], *n3b[2], *n4g[2], *n4b[2];
+  const float *l1w[2], *l1b[2], *l2w[2], *l2b[2];
+  const float *nfg, *nfb;
+  const float* hw[2][3];      // hypernetwork MLPs 1 and 2
+  const float* hb[2][3];
+  const __half *t2i_kw16[3], *t2i_vw16[3];   // image-side GEMM operands (layers 0, 1, final)
+  const __half *i2t_qw16[2], *i2t_ow16[2];
+  const __half *up1_w, *up2_w;
+  const float *up1_b, *up1_g, *up1_beta, *up2_b;
+};
+size_t sam_decoder_ws_bytes(int B, int T);
+int sam_decoder_forward(const SamDecoderWeights& w, const float* emb_nchw, int B, int s, int P, void* ws,
+                        float* mask_scores, float* mask_logits, cudaStream_t st);
+
 // ---- mask fusion (kernels.cu) : inferencer.py:79-110 --------------------------------------------------------
 int fuse_masks(const float* scores, int n_tiles, int P, const int* tile_x0, const int* tile_y0,
                int H, int W, uint8_t* keypoint_u8, uint8_t* road_u8, cudaStream_t st);

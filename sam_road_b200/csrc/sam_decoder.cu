@@ -1,0 +1,529 @@
+// sam_road_b200 :: SAM mask-decoder path (USE_SAM_DECODER: True; reference model.py:260-282,471-488,
+// sam/segment_anything/modeling/{mask_decoder.py:112-149, transformer.py:62-240,
+// prompt_encoder.py:128-205}).  Only archived configs enable it, so the design goal is exact
+// semantics with the existing building blocks, not peak speed:
+//   * image side ([B*T,256] tokens): k/v/q projections, the image->token out_proj + norm4 and the
+//     ConvTranspose upscaler run on the tcgen05 GEMM (gemm_ops.cu) with fused LN / GELU epilogues;
+//   * token side (4 output tokens per image): one thread block per image does self-attention, the
+//     token->image attention (online softmax over T keys), MLP and LayerNorms in fp32;
+//   * the token batch of 1 broadcasts against the B images from the first cross-attention on, and
+//     layer 0 REPLACES the queries by its self-attention output (transformer.py:155-161; P6).
+#include "common.cuh"
+#include "ops.h"
+
+namespace srb {
+
+namespace {
+
+constexpr int kTok = 4;      // iou token + 3 mask tokens
+constexpr int kC = 256;
+constexpr int kThreads = 256;
+
+// y[tok][n] = sum_k x[tok][k] W[n][k] + b[n]; W row-major [N,K]; x, y in shared memory
+__device__ void block_linear(const float* __restrict__ W, const float* __restrict__ b,
+                             const float* x, int ldx, float* y, int ldy, int N, int K, bool relu) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int n = warp; n < N; n += nw) {
+    float acc[kTok] = {0.f, 0.f, 0.f, 0.f};
+    const float* w = W + static_cast<size_t>(n) * K;
+    for (int k = lane; k < K; k += 32) {
+      const float wv = __ldg(w + k);
+#pragma unroll
+      for (int t = 0; t < kTok; ++t) acc[t] = fmaf(x[t * ldx + k], wv, acc[t]);
+    }
+#pragma unroll
+    for (int t = 0; t < kTok; ++t) acc[t] = warp_sum(acc[t]);
+    if (lane == 0) {
+      const float bb = b ? __ldg(b + n) : 0.f;
+#pragma unroll
+      for (int t = 0; t < kTok; ++t) {
+        const float v = acc[t] + bb;
+        y[t * ldy + n] = relu ? fmaxf(v, 0.f) : v;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// x[tok][:] = LayerNorm(x[tok][:] (+ add[tok][:])) over 256 channels, eps 1e-5 (nn.LayerNorm default)
+__device__ void block_add_layernorm(float* x, const float* add, const float* __restrict__ g,
+                                    const float* __restrict__ b) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < kTok) {
+    float v[8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = x[warp * kC + c] + (add ? add[warp * kC + c] : 0.f);
+      s += v[i];
+    }
+    const float mean = warp_sum(s) * (1.0f / kC);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q += (v[i] - mean) * (v[i] - mean);
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / kC) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = lane + 32 * i;
+      x[warp * kC + c] = (v[i] - mean) * rstd * __ldg(g + c) + __ldg(b + c);
+    }
+  }
+  __syncthreads();
+}
+
+// attention among the 4 tokens themselves (self_attn, internal dim 256 = 8 heads x 32)
+__device__ void block_self_attention(const float* q, const float* k, const float* v, float* out) {
+  // thread = (token i, channel c) over 4 x 256 = 1024 work items
+  for (int idx = threadIdx.x; idx < kTok * kC; idx += blockDim.x) {
+    const int i = idx / kC, c = idx % kC, h = c / 32;
+    float sc[kTok], mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kTok; ++j) {
+      float a = 0.f;
+      for (int d = 0; d < 32; ++d) a = fmaf(q[i * kC + h * 32 + d], k[j * kC + h * 32 + d], a);
+      sc[j] = a * 0.17677669529663687f;      // / sqrt(32), applied after QK^T (transformer.py:231-232)
+      mx = fmaxf(mx, sc[j]);
+    }
+    float l = 0.f, o = 0.f;
+#pragma unroll
+    for (int j = 0; j < kTok; ++j) {
+      const float p = expf(sc[j] - mx);
+      l += p;
+      o = fmaf(p, v[j * kC + c], o);
+    }
+    out[idx] = o / l;
+  }
+  __syncthreads();
+}
+
+struct AttnW {       // one transformer.py Attention module (fp32, token side)
+  const float *qw, *qb, *kw, *kb, *vw, *vb, *ow, *ob;
+};
+struct SamLayerW {
+  AttnW self_attn, t2i, i2t;
+  const float *n1g, *n1b, *n2g, *n2b, *n3g, *n3b;
+  const float *l1w, *l1b, *l2w, *l2b;
+};
+
+// token -> image attention for one image: q4 [4][128] (already projected), K/V [T][128] fp32 of this
+// image, 8 heads x 16; 256 threads = 32 (token, head) pairs x 8 key partitions, online softmax, then
+// a cross-partition merge in shared memory.  out [4][128].
+__device__ void block_t2i_attention(const float* q4, const float* __restrict__ K,
+                                    const float* __restrict__ V, int T, float* out, float* red) {
+  const int pair = threadIdx.x >> 3, part = threadIdx.x & 7;
+  const int i = pair >> 3, h = pair & 7;
+  float q[16];
+#pragma unroll
+  for (int d = 0; d < 16; ++d) q[d] = q4[i * 128 + h * 16 + d] * 0.25f;   // / sqrt(16)
+  float m = -INFINITY, l = 0.f, o[16];
+#pragma unroll
+  for (int d = 0; d < 16; ++d) o[d] = 0.f;
+  for (int t = part; t < T; t += 8) {
+    const float4* kp = reinterpret_cast<const float4*>(K + static_cast<size_t>(t) * 128 + h * 16);
+    float s = 0.f;
+#pragma unroll
+    for (int d4 = 0; d4 < 4; ++d4) {
+      const float4 kv = __ldg(kp + d4);
+      s = fmaf(q[4 * d4], kv.x, s); s = fmaf(q[4 * d4 + 1], kv.y, s);
+      s = fmaf(q[4 * d4 + 2], kv.z, s); s = fmaf(q[4 * d4 + 3], kv.w, s);
+    }
+    const float mn = fmaxf(m, s);
+    const float a = expf(m - mn), p = expf(s - mn);
+    l = l * a + p;
+    const float4* vp = reinterpret_cast<const float4*>(V + static_cast<size_t>(t) * 128 + h * 16);
+#pragma unroll
+    for (int d4 = 0; d4 < 4; ++d4) {
+      const float4 vv = __ldg(vp + d4);
+      o[4 * d4] = fmaf(p, vv.x, o[4 * d4] * a); o[4 * d4 + 1] = fmaf(p, vv.y, o[4 * d4 + 1] * a);
+      o[4 * d4 + 2] = fmaf(p, vv.z, o[4 * d4 + 2] * a); o[4 * d4 + 3] = fmaf(p, vv.w, o[4 * d4 + 3] * a);
+    }
+    m = mn;
+  }
+  // merge the 8 partitions of each pair: red[pair][part][18] = {m, l, o[16]}
+  float* r = red + (pair * 8 + part) * 18;
+  r[0] = m; r[1] = l;
+#pragma unroll
+  for (int d = 0; d < 16; ++d) r[2 + d] = o[d];
+  __syncthreads();
+  if (part == 0) {
+    float M = -INFINITY;
+    for (int pp = 0; pp < 8; ++pp) M = fmaxf(M, red[(pair * 8 + pp) * 18]);
+    float L = 0.f, O[16];
+#pragma unroll
+    for (int d = 0; d < 16; ++d) O[d] = 0.f;
+    for (int pp = 0; pp < 8; ++pp) {
+      const float* rr = red + (pair * 8 + pp) * 18;
+      const float a = rr[0] == -INFINITY ? 0.f : expf(rr[0] - M);
+      L = fmaf(rr[1], a, L);
+#pragma unroll
+      for (int d = 0; d < 16; ++d) O[d] = fmaf(rr[2 + d], a, O[d]);
+    }
+#pragma unroll
+    for (int d = 0; d < 16; ++d) out[i * 128 + h * 16 + d] = O[d] / L;
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// layer-0 self-attention on the (batch independent) output tokens: queries0 = norm1(self_attn(tok))
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+sam_tokens_init_kernel(const float* __restrict__ tokens, AttnW w, const float* n1g, const float* n1b,
+                       float* __restrict__ q0) {
+  __shared__ float x[kTok * kC], q[kTok * kC], k[kTok * kC], v[kTok * kC], a[kTok * kC];
+  for (int i = threadIdx.x; i < kTok * kC; i += blockDim.x) x[i] = tokens[i];
+  __syncthreads();
+  block_linear(w.qw, w.qb, x, kC, q, kC, kC, kC, false);
+  block_linear(w.kw, w.kb, x, kC, k, kC, kC, kC, false);
+  block_linear(w.vw, w.vb, x, kC, v, kC, kC, kC, false);
+  block_self_attention(q, k, v, a);
+  block_linear(w.ow, w.ob, a, kC, x, kC, kC, kC, false);        // queries = attn_out (no residual)
+  block_add_layernorm(x, nullptr, n1g, n1b);
+  for (int i = threadIdx.x; i < kTok * kC; i += blockDim.x) q0[i] = x[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// per image: [self-attn + norm1 if layer > 0] -> token->image attention -> norm2 -> MLP -> norm3 ->
+// k/v projections of the tokens for the image->token attention
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+sam_token_layer_kernel(int layer, const float* __restrict__ q_in /* [B or 1][4][256] */, int q_bcast,
+                       const float* __restrict__ tokens_pe /* [4][256] */, SamLayerW w,
+                       const float* __restrict__ K32, const float* __restrict__ V32, int T,
+                       float* __restrict__ q_out /* [B][4][256] */,
+                       float* __restrict__ k_i2t, float* __restrict__ v_i2t /* [B][4][128] */) {
+  extern __shared__ float sm[];
+  float* x = sm;                       // [4][256] queries
+  float* pe = x + kTok * kC;           // [4][256]
+  float* t0 = pe + kTok * kC;          // scratch [4][256]
+  float* t1 = t0 + kTok * kC;
+  float* t2 = t1 + kTok * kC;
+  float* t3 = t2 + kTok * kC;
+  float* hid = t3 + kTok * kC;         // [4][2048]
+  float* red = hid + kTok * 2048;      // [32*8*18]
+  const int b = blockIdx.x;
+  const float* qi = q_in + (q_bcast ? 0 : static_cast<size_t>(b) * kTok * kC);
+  for (int i = threadIdx.x; i < kTok * kC; i += blockDim.x) { x[i] = qi[i]; pe[i] = tokens_pe[i]; }
+  __syncthreads();
+  if (layer > 0) {   // q = k = queries + pe, v = queries; queries += attn; norm1 (transformer.py:162-166)
+    for (int i = threadIdx.x; i < kTok * kC; i += blockDim.x) t0[i] = x[i] + pe[i];
+    __syncthreads();
+    block_linear(w.self_attn.qw, w.self_attn.qb, t0, kC, t1, kC, kC, kC, false);
+    block_linear(w.self_attn.kw, w.self_attn.kb, t0, kC, t2, kC, kC, kC, false);
+    block_linear(w.self_attn.vw, w.self_attn.vb, x, kC, t3, kC, kC, kC, false);
+    block_self_attention(t1, t2, t3, t0);
+    block_linear(w.self_attn.ow, w.self_attn.ob, t0, kC, t1, kC, kC, kC, false);
+    block_add_layernorm(x, t1, w.n1g, w.n1b);
+  }
+  // token -> image cross attention (transformer.py:168-172): q = queries + pe
+  for (int i = threadIdx.x; i < kTok * kC; i += blockDim.x) t0[i] = x[i] + pe[i];
+  __syncthreads();
+  block_linear(w.t2i.qw, w.t2i.qb, t0, kC, t1, 128, 128, kC, false);
+  block_t2i_attention(t1, K32 + static_cast<size_t>(b) * T * 128, V32 + static_cast<size_t>(b) * T * 128, T,
+                      t2, red);
+  block_linear(w.t2i.ow, w.t2i.ob, t2, 128, t1, kC, kC, 128, false);
+  block_add_layernorm(x, t1, w.n2g, w.n2b);
+  // MLP (transformer.py:174-177)
+  block_linear(w.l1w, w.l1b, x, kC, hid, 2048, 2048, kC, true);
+  block_linear(w.l2w, w.l2b, hid, 2048, t1, kC, kC, 2048, false);
+  block_add_layernorm(x, t1, w.n3g, w.n3b);
+  // image -> token attention inputs (transformer.py:179-182): k = k_proj(queries + pe), v = v_proj(queries)
+  for (int i = threadIdx.x; i < kTok * kC; i += blockDim.x) t0[i] = x[i] + pe[i];
+  __syncthreads();
+  block_linear(w.i2t.kw, w.i2t.kb, t0, kC, t1, 128, 128, kC, false);
+  block_linear(w.i2t.vw, w.i2t.vb, x, kC, t2, 128, 128, kC, false);
+  for (int i = threadIdx.x; i < kTok * kC; i += blockDim.x)
+    q_out[static_cast<size_t>(b) * kTok * kC + i] = x[i];
+  for (int i = threadIdx.x; i < kTok * 128; i += blockDim.x) {
+    k_i2t[static_cast<size_t>(b) * kTok * 128 + i] = t1[i];
+    v_i2t[static_cast<size_t>(b) * kTok * 128 + i] = t2[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per image: final token->image attention + norm_final, then the hypernetwork MLPs of mask tokens
+// 1 and 2 (multimask_output=True keeps masks [1:], mask_decoder.py:102-106) -> hyper [B][2][32]
+// ------------------------------------------------------------------------------------------------
+struct SamFinalW {
+  AttnW attn;
+  const float *ng, *nb;
+  const float* hw[2][3];   // hypernetwork MLP i+1: layers 0..2 weights
+  const float* hb[2][3];
+};
+
+__global__ void __launch_bounds__(kThreads)
+sam_token_final_kernel(const float* __restrict__ q_in, const float* __restrict__ tokens_pe, SamFinalW w,
+                       const float* __restrict__ K32, const float* __restrict__ V32, int T,
+                       float* __restrict__ hyper) {
+  extern __shared__ float sm[];
+  float* x = sm;
+  float* t0 = x + kTok * kC;
+  float* t1 = t0 + kTok * kC;
+  float* t2 = t1 + kTok * kC;
+  float* red = t2 + kTok * kC;
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < kTok * kC; i += blockDim.x) {
+    x[i] = q_in[static_cast<size_t>(b) * kTok * kC + i];
+    t0[i] = x[i] + tokens_pe[i];
+  }
+  __syncthreads();
+  block_linear(w.attn.qw, w.attn.qb, t0, kC, t1, 128, 128, kC, false);
+  block_t2i_attention(t1, K32 + static_cast<size_t>(b) * T * 128, V32 + static_cast<size_t>(b) * T * 128, T,
+                      t2, red);
+  block_linear(w.attn.ow, w.attn.ob, t2, 128, t1, kC, kC, 128, false);
+  block_add_layernorm(x, t1, w.ng, w.nb);
+  // hypernetworks: tokens 2 and 3 of hs (mask tokens 1, 2) through MLPs 1, 2.  block_linear works on
+  // 4 "token" rows at once; run each MLP on all rows and keep the row that belongs to it.
+  for (int mi = 0; mi < 2; ++mi) {
+    block_linear(w.hw[mi][0], w.hb[mi][0], x, kC, t0, kC, kC, kC, true);
+    block_linear(w.hw[mi][1], w.hb[mi][1], t0, kC, t1, kC, kC, kC, true);
+    block_linear(w.hw[mi][2], w.hb[mi][2], t1, kC, t2, 32, 32, kC, false);
+    if (threadIdx.x < 32)
+      hyper[(static_cast<size_t>(b) * 2 + mi) * 32 + threadIdx.x] = t2[(2 + mi) * 32 + threadIdx.x];
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// image side elementwise kernels
+// ------------------------------------------------------------------------------------------------
+// keys32[m][c] = emb_nchw[b][c][t] + no_mask_embed[c]  (mask_decoder.py:126-127 with the dense prompt
+// of prompt_encoder.py:164-166)
+__global__ void sam_keys_init_kernel(const float* __restrict__ emb, const float* __restrict__ nme, int T,
+                                     long total, float* __restrict__ keys) {
+  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % kC);
+  const long m = idx / kC;
+  const int t = static_cast<int>(m % T);
+  const long b = m / T;
+  keys[idx] = emb[(b * kC + c) * T + t] + __ldg(nme + c);
+}
+// ka16 = fp16(keys + pe[t]), va16 = fp16(keys)
+__global__ void sam_keys_prep_kernel(const float* __restrict__ keys, const float* __restrict__ pe, int T,
+                                     long total, __half* __restrict__ ka16, __half* __restrict__ va16) {
+  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % kC);
+  const int t = static_cast<int>((idx / kC) % T);
+  const float v = keys[idx];
+  ka16[idx] = __float2half_rn(v + __ldg(pe + static_cast<size_t>(t) * kC + c));
+  va16[idx] = __float2half_rn(v);
+}
+// image -> token attention per image token: softmax over the 4 tokens (8 heads x 16), out fp16 [M,128]
+__global__ void sam_i2t_attention_kernel(const float* __restrict__ q32 /* [M][128] */,
+                                         const float* __restrict__ k4, const float* __restrict__ v4,
+                                         int T, long M, __half* __restrict__ out) {
+  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;   // (m, head)
+  if (idx >= M * 8) return;
+  const int h = static_cast<int>(idx & 7);
+  const long m = idx >> 3;
+  const long b = m / T;
+  const float4* qp = reinterpret_cast<const float4*>(q32 + m * 128 + h * 16);
+  float q[16];
+#pragma unroll
+  for (int d4 = 0; d4 < 4; ++d4) {
+    const float4 f = qp[d4];
+    q[4 * d4] = f.x; q[4 * d4 + 1] = f.y; q[4 * d4 + 2] = f.z; q[4 * d4 + 3] = f.w;
+  }
+  float sc[kTok], mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < kTok; ++j) {
+    const float* kp = k4 + (b * kTok + j) * 128 + h * 16;
+    float a = 0.f;
+#pragma unroll
+    for (int d = 0; d < 16; ++d) a = fmaf(q[d], __ldg(kp + d), a);
+    sc[j] = a * 0.25f;
+    mx = fmaxf(mx, sc[j]);
+  }
+  float l = 0.f, o[16];
+#pragma unroll
+  for (int d = 0; d < 16; ++d) o[d] = 0.f;
+#pragma unroll
+  for (int j = 0; j < kTok; ++j) {
+    const float p = expf(sc[j] - mx);
+    l += p;
+    const float* vp = v4 + (b * kTok + j) * 128 + h * 16;
+#pragma unroll
+    for (int d = 0; d < 16; ++d) o[d] = fmaf(p, __ldg(vp + d), o[d]);
+  }
+  const float inv = 1.0f / l;
+  __half* op = out + m * 128 + h * 16;
+#pragma unroll
+  for (int d = 0; d < 16; d += 2) *reinterpret_cast<uint32_t*>(op + d) = pack_half2(o[d] * inv, o[d + 1] * inv);
+}
+// low-res masks: rows of U2 [16M, 32] (pixel hierarchy r = ((b*s*s + i*s + j)*4 + d1)*4 + d2) dotted with
+// hyper[b][k][32] -> lr[b][y][x][k] at 4s x 4s resolution
+__global__ void sam_lowres_masks_kernel(const __half* __restrict__ u2, const float* __restrict__ hyper,
+                                        int s, long rows, float* __restrict__ lr) {
+  const long r = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const int d2 = static_cast<int>(r & 3), d1 = static_cast<int>((r >> 2) & 3);
+  const long pix = r >> 4;
+  const long b = pix / (s * s);
+  const int ij = static_cast<int>(pix % (s * s));
+  const int i = ij / s, j = ij % s;
+  const int y = (i * 2 + (d1 >> 1)) * 2 + (d2 >> 1), x = (j * 2 + (d1 & 1)) * 2 + (d2 & 1);
+  float a0 = 0.f, a1 = 0.f;
+  const __half* up = u2 + r * 32;
+  const float* h0 = hyper + b * 64;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    const float u = __half2float(up[c]);
+    a0 = fmaf(u, __ldg(h0 + c), a0);
+    a1 = fmaf(u, __ldg(h0 + 32 + c), a1);
+  }
+  const int S4 = 4 * s;
+  float* o = lr + ((b * S4 + y) * S4 + x) * 2;
+  o[0] = a0; o[1] = a1;
+}
+// F.interpolate(..., (P,P), bilinear, align_corners=False) of [B,4s,4s,2] by 4 + sigmoid -> NHWC [B,P,P,2]
+__global__ void sam_upsample4_kernel(const float* __restrict__ lr, int S4, long total, float* __restrict__ logits,
+                                     float* __restrict__ scores) {
+  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;   // (b, y, x)
+  if (idx >= total) return;
+  const int P = S4 * 4;
+  const int x = static_cast<int>(idx % P), y = static_cast<int>((idx / P) % P);
+  const long b = idx / (static_cast<long>(P) * P);
+  // source coordinate: (dst + 0.5) * (in/out) - 0.5, clamped at 0 (torch upsample_bilinear2d)
+  const float sy = fmaxf((y + 0.5f) * 0.25f - 0.5f, 0.f), sx = fmaxf((x + 0.5f) * 0.25f - 0.5f, 0.f);
+  const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
+  const int y1 = min(y0 + 1, S4 - 1), x1 = min(x0 + 1, S4 - 1);
+  const float ly = sy - y0, lx = sx - x0;
+  const float* base = lr + b * S4 * S4 * 2;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float v00 = base[(y0 * S4 + x0) * 2 + k], v01 = base[(y0 * S4 + x1) * 2 + k];
+    const float v10 = base[(y1 * S4 + x0) * 2 + k], v11 = base[(y1 * S4 + x1) * 2 + k];
+    const float v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+    if (logits) logits[idx * 2 + k] = v;
+    if (scores) scores[idx * 2 + k] = 1.0f / (1.0f + expf(-v));
+  }
+}
+
+inline int blocks_for(long n, int t) { return static_cast<int>((n + t - 1) / t); }
+
+}  // namespace
+
+struct SamDecoderWs {
+  float* keys32; __half* ka16; __half* va16; float* K32; float* V32; float* Q32; __half* att16;
+  float* qa; float* qb_; float* k4; float* v4; float* q0; float* hyper; __half* u1; __half* u2; float* lr;
+};
+
+size_t sam_decoder_ws_bytes(int B, int T) {
+  const size_t M = static_cast<size_t>(B) * T;
+  return M * 256 * 4 + M * 256 * 2 * 2 + M * 128 * 4 * 3 + M * 128 * 2 + static_cast<size_t>(B) * 4 * 256 * 4 * 2 +
+         static_cast<size_t>(B) * 4 * 128 * 4 * 2 + 4 * 256 * 4 + static_cast<size_t>(B) * 64 * 4 + M * 256 * 2 +
+         M * 4 * 128 * 2 + M * 16 * 2 * 4 + 64 * 1024;
+}
+
+int sam_decoder_forward(const SamDecoderWeights& W, const float* emb_nchw, int B, int s, int P, void* ws,
+                        float* mask_scores, float* mask_logits, cudaStream_t st) {
+  const int T = s * s;
+  const long M = static_cast<long>(B) * T;
+  auto cv = [](const SamAttnW& a) { return AttnW{a.qw, a.qb, a.kw, a.kb, a.vw, a.vb, a.ow, a.ob}; };
+  struct {
+    const float *tokens, *no_mask_embed, *dense_pe;
+    SamLayerW layer[2];
+    SamFinalW fin;
+    const __half *t2i_kw[3], *t2i_vw[3], *i2t_qw[2], *i2t_ow[2], *up1_w, *up2_w;
+    const float *t2i_kb[3], *t2i_vb[3], *i2t_qb[2], *i2t_ob[2], *n4g[2], *n4b[2];
+    const float *up1_b, *up1_g, *up1_beta, *up2_b;
+  } w;
+  w.tokens = W.tokens; w.no_mask_embed = W.no_mask_embed; w.dense_pe = W.dense_pe;
+  for (int l = 0; l < 2; ++l) {
+    w.layer[l] = SamLayerW{cv(W.self_attn[l]), cv(W.t2i[l]), cv(W.i2t[l]), W.n1g[l], W.n1b[l], W.n2g[l],
+                           W.n2b[l], W.n3g[l], W.n3b[l], W.l1w[l], W.l1b[l], W.l2w[l], W.l2b[l]};
+    w.t2i_kw[l] = W.t2i_kw16[l]; w.t2i_vw[l] = W.t2i_vw16[l];
+    w.t2i_kb[l] = W.t2i[l].kb; w.t2i_vb[l] = W.t2i[l].vb;
+    w.i2t_qw[l] = W.i2t_qw16[l]; w.i2t_ow[l] = W.i2t_ow16[l];
+    w.i2t_qb[l] = W.i2t[l].qb; w.i2t_ob[l] = W.i2t[l].ob;
+    w.n4g[l] = W.n4g[l]; w.n4b[l] = W.n4b[l];
+  }
+  w.t2i_kw[2] = W.t2i_kw16[2]; w.t2i_vw[2] = W.t2i_vw16[2];
+  w.t2i_kb[2] = W.final_attn.kb; w.t2i_vb[2] = W.final_attn.vb;
+  w.fin.attn = cv(W.final_attn); w.fin.ng = W.nfg; w.fin.nb = W.nfb;
+  for (int mi = 0; mi < 2; ++mi)
+    for (int j = 0; j < 3; ++j) { w.fin.hw[mi][j] = W.hw[mi][j]; w.fin.hb[mi][j] = W.hb[mi][j]; }
+  w.up1_w = W.up1_w; w.up2_w = W.up2_w; w.up1_b = W.up1_b; w.up1_g = W.up1_g; w.up1_beta = W.up1_beta;
+  w.up2_b = W.up2_b;
+  char* base = static_cast<char*>(ws);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* p = base + off; off += (bytes + 1023) / 1024 * 1024; return p; };
+  SamDecoderWs b;
+  b.keys32 = reinterpret_cast<float*>(take(M * 256 * 4));
+  b.ka16 = reinterpret_cast<__half*>(take(M * 256 * 2));
+  b.va16 = reinterpret_cast<__half*>(take(M * 256 * 2));
+  b.K32 = reinterpret_cast<float*>(take(M * 128 * 4));
+  b.V32 = reinterpret_cast<float*>(take(M * 128 * 4));
+  b.Q32 = reinterpret_cast<float*>(take(M * 128 * 4));
+  b.att16 = reinterpret_cast<__half*>(take(M * 128 * 2));
+  b.qa = reinterpret_cast<float*>(take(static_cast<size_t>(B) * 4 * 256 * 4));
+  b.qb_ = reinterpret_cast<float*>(take(static_cast<size_t>(B) * 4 * 256 * 4));
+  b.k4 = reinterpret_cast<float*>(take(static_cast<size_t>(B) * 4 * 128 * 4));
+  b.v4 = reinterpret_cast<float*>(take(static_cast<size_t>(B) * 4 * 128 * 4));
+  b.q0 = reinterpret_cast<float*>(take(4 * 256 * 4));
+  b.hyper = reinterpret_cast<float*>(take(static_cast<size_t>(B) * 64 * 4));
+  b.u1 = reinterpret_cast<__half*>(take(M * 256 * 2));
+  b.u2 = reinterpret_cast<__half*>(take(M * 4 * 128 * 2));
+  b.lr = reinterpret_cast<float*>(take(M * 16 * 2 * 4));
+
+  const size_t layer_smem = (6 * kTok * kC + kTok * 2048 + 32 * 8 * 18) * sizeof(float);
+  const size_t final_smem = (4 * kTok * kC + 32 * 8 * 18) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    SRB_CUDA_OK(cudaFuncSetAttribute(sam_token_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(layer_smem)));
+    attr_set = true;
+  }
+  const int Mi = static_cast<int>(M);
+
+  sam_keys_init_kernel<<<blocks_for(M * 256, 256), 256, 0, st>>>(emb_nchw, w.no_mask_embed, T, M * 256, b.keys32);
+  sam_tokens_init_kernel<<<1, kThreads, 0, st>>>(w.tokens, w.layer[0].self_attn, w.layer[0].n1g,
+                                                w.layer[0].n1b, b.q0);
+  SRB_CUDA_OK(cudaGetLastError());
+  note_launch(2);
+  const float* qcur = b.q0;
+  int q_bcast = 1;
+  float* qnext = b.qa;
+  for (int l = 0; l < 2; ++l) {
+    sam_keys_prep_kernel<<<blocks_for(M * 256, 256), 256, 0, st>>>(b.keys32, w.dense_pe, T, M * 256, b.ka16, b.va16);
+    SRB_CUDA_OK(cudaGetLastError());
+    note_launch();
+    if (int rc = gemm_f32out(b.ka16, 256, w.t2i_kw[l], 256, Mi, 128, 256, w.t2i_kb[l], nullptr, nullptr, 0, b.K32, 128, st)) return rc;
+    if (int rc = gemm_f32out(b.va16, 256, w.t2i_vw[l], 256, Mi, 128, 256, w.t2i_vb[l], nullptr, nullptr, 0, b.V32, 128, st)) return rc;
+    if (int rc = gemm_f32out(b.ka16, 256, w.i2t_qw[l], 256, Mi, 128, 256, w.i2t_qb[l], nullptr, nullptr, 0, b.Q32, 128, st)) return rc;
+    sam_token_layer_kernel<<<B, kThreads, layer_smem, st>>>(l, qcur, q_bcast, w.tokens, w.layer[l], b.K32, b.V32, T,
+                                                          qnext, b.k4, b.v4);
+    sam_i2t_attention_kernel<<<blocks_for(M * 8, 256), 256, 0, st>>>(b.Q32, b.k4, b.v4, T, M, b.att16);
+    SRB_CUDA_OK(cudaGetLastError());
+    note_launch(2);
+    // keys = norm4(keys + out_proj(attn))  (transformer.py:179-182)
+    if (int rc = gemm_ln(b.att16, 128, w.i2t_ow[l], 128, Mi, 256, 128, w.i2t_ob[l], b.keys32, w.n4g[l], w.n4b[l],
+                         1e-5f, 256, ACT_NONE, nullptr, b.keys32, nullptr, 1, 256, st)) return rc;
+    qcur = qnext; q_bcast = 0;
+    qnext = (qnext == b.qa) ? b.qb_ : b.qa;
+  }
+  // final token -> image attention + hypernetworks
+  sam_keys_prep_kernel<<<blocks_for(M * 256, 256), 256, 0, st>>>(b.keys32, w.dense_pe, T, M * 256, b.ka16, b.va16);
+  SRB_CUDA_OK(cudaGetLastError());
+  note_launch();
+  if (int rc = gemm_f32out(b.ka16, 256, w.t2i_kw[2], 256, Mi, 128, 256, w.t2i_kb[2], nullptr, nullptr, 0, b.K32, 128, st)) return rc;
+  if (int rc = gemm_f32out(b.va16, 256, w.t2i_vw[2], 256, Mi, 128, 256, w.t2i_vb[2], nullptr, nullptr, 0, b.V32, 128, st)) return rc;
+  sam_token_final_kernel<<<B, kThreads, final_smem, st>>>(qcur, w.tokens, w.fin, b.K32, b.V32, T, b.hyper);
+  SRB_CUDA_OK(cudaGetLastError());
+  note_launch();
+  // upscaler: ConvT(256->64)+LN2d+GELU, ConvT(64->32)+GELU as GEMMs (va16 = fp16(keys))
+  if (int rc = gemm_ln(b.va16, 256, w.up1_w, 256, Mi, 256, 256, w.up1_b, nullptr, w.up1_g, w.up1_beta, 1e-6f, 64,
+                       ACT_GELU, b.u1, nullptr, nullptr, 1, 256, st)) return rc;
+  if (int rc = gemm_f16out(b.u1, 64, w.up2_w, 64, 4 * Mi, 128, 64, w.up2_b, ACT_GELU, b.u2, 128, st)) return rc;
+  sam_lowres_masks_kernel<<<blocks_for(16 * M, 256), 256, 0, st>>>(b.u2, b.hyper, s, 16 * M, b.lr);
+  sam_upsample4_kernel<<<blocks_for(static_cast<long>(B) * P * P, 256), 256, 0, st>>>(
+      b.lr, 4 * s, static_cast<long>(B) * P * P, mask_logits, mask_scores);
+  SRB_CUDA_OK(cudaGetLastError());
+  note_launch(2);
+  return 0;
+}
+
+}  // namespace srb

@@ -29,6 +29,8 @@ _VIT = {  # model.py:198-218
     "vit_l": (1024, 24, 16, (5, 11, 17, 23)),
     "vit_h": (1280, 32, 16, (7, 15, 23, 31)),
 }
+# persistent buffers (state_dict entries that are not parameters): the random-Fourier PE matrix
+BUFFER_KEYS = ("prompt_encoder.pe_layer.positional_encoding_gaussian_matrix",)
 _TOPO_VERSION = {"no_offset": _lib.TOPO_NO_OFFSET, "no_transformer": _lib.TOPO_NO_TRANSFORMER}
 
 
@@ -75,14 +77,54 @@ def param_shapes(config) -> Dict[str, Tuple[int, ...]]:
     sh[e + "neck.2.weight"] = (256, 256, 3, 3)
     sh[e + "neck.3.weight"] = (256,); sh[e + "neck.3.bias"] = (256,)
     if _cfg_get(config, "USE_SAM_DECODER", False):
-        raise NotImplementedError(
-            "USE_SAM_DECODER: True (SAM TwoWayTransformer mask decoder, reference model.py:260-282) "
-            "is not built in sam_road_b200 yet; every shipped config/toponet_*.yaml uses the naive "
-            "map_decoder (USE_SAM_DECODER: False)")
-    for idx, (cin, cout) in zip((0, 3, 5, 7), ((256, 128), (128, 64), (64, 32), (32, 2))):
-        sh[f"map_decoder.{idx}.weight"] = (cin, cout, 2, 2)
-        sh[f"map_decoder.{idx}.bias"] = (cout,)
-    sh["map_decoder.1.weight"] = (128,); sh["map_decoder.1.bias"] = (128,)
+        # prompt_encoder (only no_mask_embed and the PE matrix are used on this path, the rest must
+        # exist for strict checkpoint loading) + mask_decoder (model.py:260-282)
+        pe = "prompt_encoder."
+        sh[pe + BUFFER_KEYS[0][len(pe):]] = (2, 128)
+        for i in range(4):
+            sh[pe + f"point_embeddings.{i}.weight"] = (1, 256)
+        sh[pe + "not_a_point_embed.weight"] = (1, 256)
+        sh[pe + "mask_downscaling.0.weight"] = (4, 1, 2, 2); sh[pe + "mask_downscaling.0.bias"] = (4,)
+        sh[pe + "mask_downscaling.1.weight"] = (4,); sh[pe + "mask_downscaling.1.bias"] = (4,)
+        sh[pe + "mask_downscaling.3.weight"] = (16, 4, 2, 2); sh[pe + "mask_downscaling.3.bias"] = (16,)
+        sh[pe + "mask_downscaling.4.weight"] = (16,); sh[pe + "mask_downscaling.4.bias"] = (16,)
+        sh[pe + "mask_downscaling.6.weight"] = (256, 16, 1, 1); sh[pe + "mask_downscaling.6.bias"] = (256,)
+        sh[pe + "no_mask_embed.weight"] = (1, 256)
+        md = "mask_decoder."
+
+        def attn(prefix, internal):
+            for nm in ("q_proj", "k_proj", "v_proj"):
+                sh[prefix + nm + ".weight"] = (internal, 256); sh[prefix + nm + ".bias"] = (internal,)
+            sh[prefix + "out_proj.weight"] = (256, internal); sh[prefix + "out_proj.bias"] = (256,)
+        for l in range(2):
+            p = f"{md}transformer.layers.{l}."
+            attn(p + "self_attn.", 256)
+            attn(p + "cross_attn_token_to_image.", 128)
+            attn(p + "cross_attn_image_to_token.", 128)
+            for n in (1, 2, 3, 4):
+                sh[p + f"norm{n}.weight"] = (256,); sh[p + f"norm{n}.bias"] = (256,)
+            sh[p + "mlp.lin1.weight"] = (2048, 256); sh[p + "mlp.lin1.bias"] = (2048,)
+            sh[p + "mlp.lin2.weight"] = (256, 2048); sh[p + "mlp.lin2.bias"] = (256,)
+        attn(md + "transformer.final_attn_token_to_image.", 128)
+        sh[md + "transformer.norm_final_attn.weight"] = (256,); sh[md + "transformer.norm_final_attn.bias"] = (256,)
+        sh[md + "iou_token.weight"] = (1, 256); sh[md + "mask_tokens.weight"] = (3, 256)
+        sh[md + "output_upscaling.0.weight"] = (256, 64, 2, 2); sh[md + "output_upscaling.0.bias"] = (64,)
+        sh[md + "output_upscaling.1.weight"] = (64,); sh[md + "output_upscaling.1.bias"] = (64,)
+        sh[md + "output_upscaling.3.weight"] = (64, 32, 2, 2); sh[md + "output_upscaling.3.bias"] = (32,)
+        for i in range(3):
+            m = f"{md}output_hypernetworks_mlps.{i}.layers."
+            sh[m + "0.weight"] = (256, 256); sh[m + "0.bias"] = (256,)
+            sh[m + "1.weight"] = (256, 256); sh[m + "1.bias"] = (256,)
+            sh[m + "2.weight"] = (32, 256); sh[m + "2.bias"] = (32,)
+        m = md + "iou_prediction_head.layers."
+        sh[m + "0.weight"] = (256, 256); sh[m + "0.bias"] = (256,)
+        sh[m + "1.weight"] = (256, 256); sh[m + "1.bias"] = (256,)
+        sh[m + "2.weight"] = (3, 256); sh[m + "2.bias"] = (3,)
+    else:
+        for idx, (cin, cout) in zip((0, 3, 5, 7), ((256, 128), (128, 64), (64, 32), (32, 2))):
+            sh[f"map_decoder.{idx}.weight"] = (cin, cout, 2, 2)
+            sh[f"map_decoder.{idx}.bias"] = (cout,)
+        sh["map_decoder.1.weight"] = (128,); sh["map_decoder.1.bias"] = (128,)
     t = "topo_net."
     sh[t + "feature_proj.weight"] = (128, 256); sh[t + "feature_proj.bias"] = (128,)
     sh[t + "pair_proj.weight"] = (128, 258); sh[t + "pair_proj.bias"] = (128,)
@@ -114,6 +156,16 @@ def _register(root: nn.Module, key: str, p: nn.Parameter) -> None:
             node.add_module(name, _Node())
         node = node._modules[name]
     node.register_parameter(parts[-1], p)
+
+
+def _register_buffer(root: nn.Module, key: str, t: torch.Tensor) -> None:
+    parts = key.split(".")
+    node = root
+    for name in parts[:-1]:
+        if name not in node._modules:
+            node.add_module(name, _Node())
+        node = node._modules[name]
+    node.register_buffer(parts[-1], t, persistent=True)
 
 
 try:  # the reference derives from LightningModule (model.py:190); use it when importable
@@ -150,7 +202,10 @@ class SAMRoad(_Base):
                 for d in shape[1:]:
                     fan_in *= d
                 init = (torch.rand(shape, generator=gen) * 2 - 1) / max(1.0, fan_in) ** 0.5
-            _register(self, key, nn.Parameter(init, requires_grad=False))
+            if key in BUFFER_KEYS:
+                _register_buffer(self, key, torch.randn(shape, generator=gen))
+            else:
+                _register(self, key, nn.Parameter(init, requires_grad=False))
         self.register_buffer("pixel_mean", torch.tensor([123.675, 116.28, 103.53]).view(-1, 1, 1), False)
         self.register_buffer("pixel_std", torch.tensor([58.395, 57.12, 57.375]).view(-1, 1, 1), False)
         self._handles: Dict[int, int] = {}     # cuda device index -> samroad_handle_t
@@ -180,7 +235,7 @@ class SAMRoad(_Base):
                         t = sd[k][None, None]
                         sd[k] = F.interpolate(t, (2 * s - 1, t.shape[-1]), mode="bilinear",
                                               align_corners=False)[0, 0]
-        own = dict(self.named_parameters())
+        own = dict(self.named_parameters())   # like the reference: parameters only (model.py:378)
         matched = {k: v for k, v in sd.items() if k in own and own[k].shape == v.shape}
         self.matched_param_names = set(matched)
         self.load_state_dict(matched, strict=False)
@@ -223,7 +278,9 @@ class SAMRoad(_Base):
             self._handles[idx] = h.value
         if self._synced_version.get(idx) != self._weights_version:
             h = self._handles[idx]
-            for key, p in self.named_parameters():
+            tensors = list(self.named_parameters()) + [(k, b) for k, b in self.named_buffers()
+                                                        if k in BUFFER_KEYS]
+            for key, p in tensors:
                 t = p.detach().to(device="cpu", dtype=torch.float32).contiguous()
                 shape = (C.c_int64 * t.dim())(*t.shape)
                 _lib.check(lib.samroad_load_tensor(h, key.encode(), t.data_ptr(), shape, t.dim()),

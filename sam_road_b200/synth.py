@@ -15,12 +15,16 @@ import torch
 
 from .model import param_shapes
 
-_NORM_WEIGHTS = ("image_encoder.neck.1.weight", "image_encoder.neck.3.weight", "map_decoder.1.weight")
+_NORM_WEIGHTS = ("image_encoder.neck.1.weight", "image_encoder.neck.3.weight", "map_decoder.1.weight",
+                 "mask_decoder.output_upscaling.1.weight", "prompt_encoder.mask_downscaling.1.weight",
+                 "prompt_encoder.mask_downscaling.4.weight")
 
 
 def _is_norm(key: str) -> bool:
     stem = key.rsplit(".", 1)[0]
-    return stem.endswith("norm1") or stem.endswith("norm2") or (stem + ".weight") in _NORM_WEIGHTS
+    last = stem.rsplit(".", 1)[-1]
+    return last in ("norm1", "norm2", "norm3", "norm4", "norm_final_attn") or \
+        (stem + ".weight") in _NORM_WEIGHTS
 
 
 def make_state_dict(config, seed: int = 0, logit_gain: float = 1.0) -> Dict[str, torch.Tensor]:
@@ -35,7 +39,9 @@ def make_state_dict(config, seed: int = 0, logit_gain: float = 1.0) -> Dict[str,
 
     for key, shape in shapes.items():
         leaf = key.rsplit(".", 1)[1]
-        if key.endswith("pos_embed") or "rel_pos" in key:
+        if key.endswith("positional_encoding_gaussian_matrix"):
+            t = torch.randn(shape, generator=gen)           # PositionEmbeddingRandom, scale 1.0
+        elif key.endswith("pos_embed") or "rel_pos" in key:
             t = 0.02 * torch.randn(shape, generator=gen)
         elif _is_norm(key):
             t = (1.0 + 0.1 * torch.randn(shape, generator=gen)) if leaf == "weight" \
@@ -54,7 +60,8 @@ def make_state_dict(config, seed: int = 0, logit_gain: float = 1.0) -> Dict[str,
             t = uniform(shape, 1.0 / math.sqrt(int(np.prod(wshape[1:]))))
         sd[key] = t
     for key in ("map_decoder.7.weight", "map_decoder.7.bias", "topo_net.output_proj.weight",
-                "topo_net.output_proj.bias"):
+                "topo_net.output_proj.bias", "mask_decoder.output_hypernetworks_mlps.1.layers.2.weight",
+                "mask_decoder.output_hypernetworks_mlps.2.layers.2.weight"):
         if key in sd:
             sd[key] = sd[key] * logit_gain
     return sd

@@ -107,6 +107,17 @@ def test_samroad_module_mirrors_reference_interface(tmp_path):
     assert "image_encoder.blocks.0.attn.rel_pos_h" in net2.matched_param_names
 
 
+def test_sam_decoder_state_dict_keys():
+    cfg = dict(SAM_VERSION="vit_b", PATCH_SIZE=256, USE_SAM_DECODER=True)
+    net = SAMRoad(cfg)
+    sd = synth.make_state_dict(cfg, seed=0)
+    keys = set(net.state_dict().keys())
+    assert keys == set(sd.keys()) and len(keys) == 350
+    assert "prompt_encoder.pe_layer.positional_encoding_gaussian_matrix" in keys      # persistent buffer
+    assert "map_decoder.0.weight" not in keys and "mask_decoder.iou_token.weight" in keys
+    assert not net.load_state_dict(sd, strict=True).missing_keys
+
+
 def test_addict_style_config_missing_keys():
     class Cfg(dict):
         def __getattr__(self, k):

@@ -38,8 +38,8 @@ def _fp32_oracle_math(report_dir):
     json.dump(old, open(path, "w"), indent=1, sort_keys=True)
 
 
-def _config(patch, version="vit_b", topo="normal", lora=0):
-    return dict(SAM_VERSION=version, PATCH_SIZE=patch, USE_SAM_DECODER=False,
+def _config(patch, version="vit_b", topo="normal", lora=0, samdec=False):
+    return dict(SAM_VERSION=version, PATCH_SIZE=patch, USE_SAM_DECODER=samdec,
                 ENCODER_LORA=lora > 0, LORA_RANK=lora, TOPONET_VERSION=topo, NO_SAM=False)
 
 
@@ -62,9 +62,11 @@ def _maxabs(a, b):
     ("vitb_512", 512, "vit_b", 2, 0),
     ("vitb_256_lora4", 256, "vit_b", 1, 4),
     ("vith_256", 256, "vit_h", 1, 0),
+    ("vitb_256_samdec", 256, "vit_b", 3, 0),       # USE_SAM_DECODER: True (archived configs)
+    ("vitb_512_samdec", 512, "vit_b", 2, 0),
 ])
 def test_encode_and_topo_parity(name, patch, version, B, lora):
-    cfg = _config(patch, version, lora=lora)
+    cfg = _config(patch, version, lora=lora, samdec=name.endswith("samdec"))
     spec, sd, net = _build(cfg)
     rgb_u8 = synth.make_tiles(B, patch, seed=3).to(DEV)
     rgb = rgb_u8.float()

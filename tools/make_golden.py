@@ -29,8 +29,8 @@ OUT = os.path.join(ROOT, "tests", "golden")
 ORACLE_TOL = 2e-5
 
 
-def _cfg(patch, version="vit_b", topo="normal", lora=0):
-    return dict(SAM_VERSION=version, PATCH_SIZE=patch, USE_SAM_DECODER=False, ENCODER_LORA=lora > 0,
+def _cfg(patch, version="vit_b", topo="normal", lora=0, samdec=False):
+    return dict(SAM_VERSION=version, PATCH_SIZE=patch, USE_SAM_DECODER=samdec, ENCODER_LORA=lora > 0,
                 LORA_RANK=lora, TOPONET_VERSION=topo, NO_SAM=False, FOCAL_LOSS=False)
 
 
@@ -154,6 +154,7 @@ def main():
     model_fixture("vitb_256", _cfg(256), seed=0, n_points=24)
     model_fixture("vitb_512", _cfg(512), seed=1, n_points=40)
     model_fixture("vitb_256_lora4", _cfg(256, lora=4), seed=2, n_points=16)
+    model_fixture("vitb_256_samdec", _cfg(256, samdec=True), seed=3, n_points=16)
     toponet_fixture()
     tileloop_fixture()
 
