@@ -154,13 +154,14 @@ def fuse_masks_device(scores: torch.Tensor, tiles: Sequence[TileInfo], H: int, W
 
 
 def infer_one_img(net, img: np.ndarray, config, device: Optional[torch.device] = None,
-                  group=None, timings: Optional[dict] = None):
+                  group=None, timings: Optional[dict] = None, shard: bool = True):
     """Whole-scene inference (inferencer.py:61-234).
 
     img: uint8 [H,W,3] RGB.  Returns (pred_nodes [N,2] (r,c), pred_edges [E,2], fused_keypoint_mask
-    uint8 [H,W], fused_road_mask uint8 [H,W]) -- identical on every rank when run distributed."""
+    uint8 [H,W], fused_road_mask uint8 [H,W]) -- identical on every rank when run distributed.
+    `shard=False` makes a rank process the whole scene alone even if torch.distributed is up."""
     import torch.distributed as dist
-    distributed = dist.is_available() and dist.is_initialized()
+    distributed = shard and dist.is_available() and dist.is_initialized()
     rank = dist.get_rank(group) if distributed else 0
     world = dist.get_world_size(group) if distributed else 1
     if device is None:
