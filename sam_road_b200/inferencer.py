@@ -212,7 +212,7 @@ def infer_one_img(net, img: np.ndarray, config, device: Optional[torch.device] =
         def pad(a):
             return np.pad(a, [(0, nmax - a.shape[0])] + [(0, 0)] * (a.ndim - 1))
         for bi, b0 in enumerate(range(0, len(my_tiles), bs)):
-            q = queries[lo + b0: lo + b0 + bs]
+            q = queries[lo + b0: min(lo + b0 + bs, hi)]     # this rank's tiles of the batch only
             if max(x[1].shape[0] for x in q) == 0:       # inferencer.py:188-189
                 continue
             pts = torch.as_tensor(np.stack([pad(x[1]) for x in q]), device=device)
