@@ -103,12 +103,32 @@ def time_cpu_oracle(n_tiles: int, steps: int, warmup: int):
     import torch
     from oracle import samroad_oracle as O          # the only place bench.py executes oracle/
     from sam_road_b200 import synth
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     spec = O.ModelSpec.from_config(CONFIG)
     sd = synth.make_state_dict(CONFIG, seed=0)
     rgb = synth.make_tiles(n_tiles, 512, seed=11, dtype=torch.float32)
     pts, prs, val = synth.make_topo_inputs(n_tiles, 512, POINTS_PER_TILE, seed=12, ragged=False)
+    # all the host threads the process can really use: the affinity mask / cgroup quota may be far
+    # below os.cpu_count() on a shared box, and oversubscribed eager PyTorch is several times slower,
+    # so probe a few thread counts on one tile and keep the fastest
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            avail = max(1, min(avail, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    cands = sorted({avail, min(avail, 64), min(avail, 32), min(avail, 16), min(avail, 8)}, reverse=True)
+    best_t, cores = None, avail
+    with torch.no_grad():
+        for c in cands:
+            torch.set_num_threads(c)
+            O.image_encoder(O.normalize_rgb(rgb[:1]), sd, spec)          # warm
+            t0 = time.perf_counter()
+            O.image_encoder(O.normalize_rgb(rgb[:1]), sd, spec)
+            dt = time.perf_counter() - t0
+            if best_t is None or dt < best_t:
+                best_t, cores = dt, c
+    torch.set_num_threads(cores)
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
@@ -145,7 +165,7 @@ def run_reference(args):
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -312,12 +332,43 @@ def run_native(args):
         "kernels": shares,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+class _JsonStdout:
+    """Keep stdout clean for the single JSON line: libraries (NCCL prints its version banner on the
+    first communicator) write to fd 1, so fd 1 is pointed at stderr for the run and the JSON line goes
+    to the saved original stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.fd = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line: str):
+        os.write(self.fd, (line + "\n").encode())
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.fd, 1)
+        os.close(self.fd)
+
+
+_OUT = None
+
+
+def emit(line: str):
+    if _OUT is not None:
+        _OUT.emit(line)
+    else:
+        print(line, flush=True)
+
+
 def main():
+    global _OUT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -328,10 +379,12 @@ def main():
                     help="tiles per step of the CPU reference arm (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_native(args)
+    with _JsonStdout() as out:
+        _OUT = out
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_native(args)
 
 
 if __name__ == "__main__":
