@@ -523,7 +523,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
               const float p0 = ex2_approx(y[c * 32 + i + 0] + sub);
               const float p1 = ex2_approx(y[c * 32 + i + 1] + sub);
               const float p2 = ex2_approx(y[c * 32 + i + 2] + sub);
-              const float p3 = ex2_approx(y[c * 32 + i + 3] + sub);
+              const float p3 = ex2_poly3(y[c * 32 + i + 3] + sub);   // FMA-pipe exp (1 in 4)
               ls0 += p0; ls1 += p1; ls2 += p2; ls3 += p3;
               pk[c * 16 + i / 2] = pack_half2(p0, p1);
               pk[c * 16 + i / 2 + 1] = pack_half2(p2, p3);

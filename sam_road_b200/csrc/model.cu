@@ -129,6 +129,9 @@ struct samroad_ctx {
   size_t ws_bytes = 0;
   // staging for the host-buffer entry point
   void* stage_in = nullptr;  size_t stage_in_bytes = 0;
+  cudaStream_t s_compute = nullptr, s_copy = nullptr;   // host-buffer entry point: compute / D2H overlap
+  cudaEvent_t ev_emb = nullptr, ev_scores = nullptr;
+  bool hook_after_neck = false;                          // record ev_emb once the embeddings are final
   float* stage_scores = nullptr; size_t stage_scores_bytes = 0;
   float* stage_emb = nullptr; size_t stage_emb_bytes = 0;
 };
@@ -391,6 +394,8 @@ extern "C" int samroad_destroy(samroad_handle_t h) {
   for (void* p : h->weight_allocs) cudaFree(p);
   if (h->ws) cudaFree(h->ws);
   if (h->sam_ws) cudaFree(h->sam_ws);
+  if (h->s_compute) { cudaStreamDestroy(h->s_compute); cudaStreamDestroy(h->s_copy);
+                      cudaEventDestroy(h->ev_emb); cudaEventDestroy(h->ev_scores); }
   if (h->stage_in) cudaFree(h->stage_in);
   if (h->stage_scores) cudaFree(h->stage_scores);
   if (h->stage_emb) cudaFree(h->stage_emb);
@@ -759,6 +764,7 @@ extern "C" int samroad_encode_masks(samroad_handle_t h, const void* rgb, int rgb
                 1e-6f, 256, ACT_NONE, w.FEAT, nullptr, image_embeddings, T, 256, st));
 
   // naive map decoder (model.py:286-295, 490-491) as three GEMMs, pixel shuffle by row indexing
+  if (h->hook_after_neck) SRB_CUDA_OK(cudaEventRecord(h->ev_emb, st));   // embeddings are final here
   if ((mask_scores || mask_logits) && h->cfg.use_sam_decoder) {
     // SAM mask decoder (model.py:471-488): null prompts, TwoWayTransformer, upscaler, x4 bilinear
     SRB_TRY(ensure_bytes(&h->sam_ws, &h->sam_ws_bytes, sam_decoder_ws_bytes(B, T)));
@@ -960,30 +966,44 @@ extern "C" int samroad_infer_batch_host(samroad_handle_t h, const void* rgb_host
   SRB_TRY(ensure_bytes(reinterpret_cast<void**>(&h->stage_scores), &h->stage_scores_bytes, sc_bytes));
   SRB_TRY(ensure_bytes(reinterpret_cast<void**>(&h->stage_emb), &h->stage_emb_bytes, em_bytes));
   char* base = static_cast<char*>(h->stage_in);
-  cudaStream_t st = nullptr;
+  // compute on one stream, result downloads on a second one: the embeddings go back while the mask
+  // decoder runs, the mask scores while TopoNet runs
+  if (!h->s_compute) {
+    SRB_CUDA_OK(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
+    SRB_CUDA_OK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+    SRB_CUDA_OK(cudaEventCreateWithFlags(&h->ev_emb, cudaEventDisableTiming));
+    SRB_CUDA_OK(cudaEventCreateWithFlags(&h->ev_scores, cudaEventDisableTiming));
+  }
+  cudaStream_t st = h->s_compute, sc = h->s_copy;
   SRB_CUDA_OK(cudaMemcpyAsync(base, rgb_host, in_bytes, cudaMemcpyHostToDevice, st));
   if (topo) {
     SRB_CUDA_OK(cudaMemcpyAsync(base + o_pts, points_host, pts_bytes, cudaMemcpyHostToDevice, st));
     SRB_CUDA_OK(cudaMemcpyAsync(base + o_prs, pairs_host, prs_bytes, cudaMemcpyHostToDevice, st));
     SRB_CUDA_OK(cudaMemcpyAsync(base + o_val, valid_host, val_bytes, cudaMemcpyHostToDevice, st));
   }
-  SRB_TRY(samroad_encode_masks(h, base, rgb_dtype, B, mask_scores_host ? h->stage_scores : nullptr,
-                               nullptr, h->stage_emb, st));
-  if (mask_scores_host)
-    SRB_CUDA_OK(cudaMemcpyAsync(mask_scores_host, h->stage_scores, sc_bytes, cudaMemcpyDeviceToHost,
-                                st));
-  if (image_embeddings_host)
-    SRB_CUDA_OK(cudaMemcpyAsync(image_embeddings_host, h->stage_emb, em_bytes,
-                                cudaMemcpyDeviceToHost, st));
+  h->hook_after_neck = true;
+  const int rc_enc = samroad_encode_masks(h, base, rgb_dtype, B, mask_scores_host ? h->stage_scores : nullptr,
+                                          nullptr, h->stage_emb, st);
+  h->hook_after_neck = false;
+  if (rc_enc != 0) return rc_enc;
+  if (image_embeddings_host) {
+    SRB_CUDA_OK(cudaStreamWaitEvent(sc, h->ev_emb, 0));
+    SRB_CUDA_OK(cudaMemcpyAsync(image_embeddings_host, h->stage_emb, em_bytes, cudaMemcpyDeviceToHost, sc));
+  }
+  if (mask_scores_host) {
+    SRB_CUDA_OK(cudaEventRecord(h->ev_scores, st));
+    SRB_CUDA_OK(cudaStreamWaitEvent(sc, h->ev_scores, 0));
+    SRB_CUDA_OK(cudaMemcpyAsync(mask_scores_host, h->stage_scores, sc_bytes, cudaMemcpyDeviceToHost, sc));
+  }
   if (topo) {
     SRB_TRY(samroad_toponet(h, h->stage_emb, base + o_pts, pts_dtype, base + o_prs, pairs_dtype,
                             reinterpret_cast<const uint8_t*>(base + o_val), B, N, Ns, Np, nullptr,
                             reinterpret_cast<float*>(base + o_ts), st));
     if (topo_scores_host)
-      SRB_CUDA_OK(cudaMemcpyAsync(topo_scores_host, base + o_ts, ts_bytes, cudaMemcpyDeviceToHost,
-                                  st));
+      SRB_CUDA_OK(cudaMemcpyAsync(topo_scores_host, base + o_ts, ts_bytes, cudaMemcpyDeviceToHost, st));
   }
   SRB_CUDA_OK(cudaStreamSynchronize(st));
+  SRB_CUDA_OK(cudaStreamSynchronize(sc));
   return 0;
 }
 
