@@ -147,9 +147,14 @@ int samroad_op_attention(const void* qkv16, const float* qkv_bias, const float* 
 /* Test hook: route samroad_op_attention / the encoder through the fp32 SIMT attention kernel (the
  * independent on-device checker of the tcgen05 kernel).  Not for production use. */
 void samroad_debug_force_simt_attention(int on);
-/* Test hook: route every GEMM through the 1-CTA kernels (the 2-CTA cta_group::2 kernel is then
- * checked against them). */
+/* Test hook (bit mask): bit 0 routes every GEMM through the 1-CTA kernels (the 2-CTA cta_group::2
+ * kernel is then checked against them); bit 1 routes the in-place fp32 shortcut GEMMs through the
+ * register-path epilogue instead of the TMA one; bit 2 selects the TMA load+store variant of that
+ * epilogue (bit-identical to the register path) instead of the default TMA reduce-add. */
 void samroad_debug_disable_2cta_gemm(int off);
+/* Debug hook: device buffer of 128 int64 receiving clock64 stamps of CTA 0's first work unit in the
+ * tcgen05 attention kernel (softmax warp phases, MMA issue times); NULL disables. */
+void samroad_debug_attention_trace(void* dev_buf);
 
 #ifdef __cplusplus
 }

@@ -224,6 +224,8 @@ int pack_rel_table(const float* rel_h, const float* rel_w, int win, int hd, __ha
 }
 
 static bool g_force_simt = false;
+static long long* g_att_trace = nullptr;
+void attention_set_trace(long long* p) { g_att_trace = p; }
 void attention_force_simt(bool on) { g_force_simt = on; }
 
 template <bool kWindow, int WIN>
@@ -258,6 +260,7 @@ static int launch_attention_tc(const __half* qkv, const float* qkv_bias, const _
   p.scale_log2e = 0.125f * 1.4426950408889634f;
   const int units = kWindow ? B * p.nwin * p.nwin * heads : B * (T / 256) * heads;
   p.num_units = units;
+  p.trace = g_att_trace;
   const int grid = units < device_sm_count() ? units : device_sm_count();   // persistent CTAs
   kern<<<grid, kAtcThreads, AtcSmem<kWindow>::kBytes, st>>>(tmQKV, tmTab, p);
   SRB_CUDA_OK(cudaGetLastError());

@@ -4,8 +4,9 @@
 // Persistent CTAs (grid = #SMs) loop over work units (image, window, head) / (image, head, 256-query
 // slab).  12 warps = 3 warpgroups:
 //   warp 0        TMA producer: rel-pos table (once), per unit Q (256 rows) and K/V blocks of 128 keys
-//   warp 1        TMEM allocator + single-thread tcgen05.mma issuer (event driven)
-//   warps 2-3     idle (complete the control warpgroup, which gives its registers away)
+//   warp 1        TMEM allocator; lane 0 issues the tcgen05.mma of softmax group 0 (blocking waits)
+//   warp 2        lane 0 issues the tcgen05.mma of softmax group 1
+//   warp 3        idle (completes the control warpgroup, which gives its registers away)
 //   warps 4-7     softmax group 0 (query rows   0..127 of the unit, one row per thread)
 //   warps 8-11    softmax group 1 (query rows 128..255)
 //
@@ -61,6 +62,7 @@ struct AtcParams {
   int nwin;                // windows per side (window mode)
   int num_units;
   float scale_log2e;       // head_dim^-0.5 * log2(e)
+  long long* trace;        // debug: clock64 stamps of CTA 0 (softmax warp 4: 8 per block; MMA thread), or null
 };
 
 struct AtcUnit {
@@ -120,7 +122,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
   uint8_t* sP = smem + SM::kOffP;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::kOffBar);
   uint64_t* tab_full = bars + 0;
-  uint64_t* t_ready = bars + 1;
   uint64_t* kv_fixed = bars + 2;
   uint64_t* q_full = bars + 3;                  // [2]
   uint64_t* q_empty = bars + 5;                 // [2]
@@ -130,7 +131,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
   uint64_t* s_free = bars + 15;                 // [2]
   uint64_t* p_ready = bars + 17;                // [2]
   uint64_t* pv_done = bars + 19;                // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+  uint64_t* t_ready = bars + 21;                // [2]
+  uint64_t* stagger = bars + 23;                // group 0 -> group 1 issuer: half-block phase offset
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -140,10 +143,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmTab);
     mbar_init(tab_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
-    mbar_init(t_ready, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 2); mbar_init(&t_ready[i], 1); }
     mbar_init(kv_fixed, 256);
-    for (int i = 0; i < kAtcKVStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    mbar_init(stagger, 128);
+    for (int i = 0; i < kAtcKVStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 2); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_ready[i], 1);
       mbar_init(&s_free[i], 128);
@@ -212,109 +215,101 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
           }
         }
       }
-    } else if (warp == 1 && lane == 0) {
-      // =========================== MMA issuer ===========================
+    } else if ((warp == 1 || warp == 2) && lane == 0) {
+      // =========================== MMA issuers: one thread per softmax group ===========================
+      // For one group the order of events is fixed -- S(0), then for every block: S(jb+1) once the
+      // group has pulled S(jb) into registers (s_free), PV(jb) once P(jb) is in smem (p_ready) -- so
+      // each issuer uses plain blocking waits; nothing polls.
+      const int g = warp - 1;
       mbar_wait(tab_full, 0);
       int ui = 0;
-      int wcnt[2] = {0, 0};     // writes (T or S) issued into each group's S region so far
-      int bcnt[2] = {0, 0};     // blocks completed by each group in earlier units
+      int wcnt = 0;      // writes (T or S) issued into this group's S region so far
+      int bcnt = 0;      // blocks completed by this group in earlier units
+      constexpr uint32_t idT = umma_idesc_f16(128, NTAB);
+      constexpr uint32_t idPV = umma_idesc_f16_bmn(128, 64);
       for (int u = blockIdx.x; u < p.num_units; u += gridDim.x, ++ui) {
         const AtcUnit un = atc_decode<kWindow, WIN>(u, p);
-        const int nact = atc_group1_active<kWindow, WIN>(un, p) ? 2 : 1;
+        const bool active = g == 0 || atc_group1_active<kWindow, WIN>(un, p);
         const int qs = ui % QST;
         const uint8_t* sQu = sQ + qs * 32768;
         const int ks = ui % kAtcKVStages;                  // window mode: K/V stage of this unit
+        const int gb0 = ui * NBLK;                         // global mode: ring position of block 0
         mbar_wait(&q_full[qs], (ui / QST) & 1);
+        if (!active) {     // nothing to compute, but keep the 2-arrival barriers and the pacing moving
+          mbar_arrive(&t_ready[g]);
+          mbar_arrive(&q_empty[qs]);
+          if constexpr (kWindow) mbar_arrive(&kv_empty[ks]);
+          continue;
+        }
         tc_fence_after_sync();
-        {   // rel-pos projections T_g = Q_g * Tab^T into the S regions
-          constexpr uint32_t idT = umma_idesc_f16(128, NTAB);
-          const uint64_t bdesc = umma_desc_k128(smem_u32(sTab));
-          for (int g = 0; g < nact; ++g) {
-            if (wcnt[g] > 0) {
-              mbar_wait(&s_free[g], (wcnt[g] - 1) & 1);
-              tc_fence_after_sync();
-            }
-            const uint64_t adesc = umma_desc_k128(smem_u32(sQu + g * 16384));
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16_ss(tmem_base + g * 128, adesc + 2 * k, bdesc + 2 * k, idT, k != 0 ? 1u : 0u);
-            wcnt[g]++;
+        auto wait_s_region = [&]() {       // previous contents of the S region consumed?
+          if (wcnt > 0) {
+            mbar_wait(&s_free[g], (wcnt - 1) & 1);
+            tc_fence_after_sync();
           }
-          umma_commit(t_ready);
+        };
+        auto issue_s = [&](int jb) {
+          if constexpr (kWindow) {
+            if (jb == 0) mbar_wait(&kv_full[ks], (ui / kAtcKVStages) & 1);
+          } else {
+            const int gbk = gb0 + jb;
+            mbar_wait(&kv_full[gbk % kAtcKVStages], (gbk / kAtcKVStages) & 1);
+          }
+          wait_s_region();
+          tc_fence_after_sync();
+          const int nkeys = (kWindow && jb == NBLK - 1) ? kLastMma : 128;
+          const uint32_t kbase = kWindow ? smem_u32(sKV + ks * SM::kKVStage + jb * 16384)
+                                         : smem_u32(sKV + ((gb0 + jb) % kAtcKVStages) * SM::kKVStage);
+          const uint32_t idS = umma_idesc_f16(128, nkeys);
+          const uint64_t adesc = umma_desc_k128(smem_u32(sQu + g * 16384));
+          const uint64_t bdesc = umma_desc_k128(kbase);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ss(tmem_base + g * 128, adesc + 2 * k, bdesc + 2 * k, idS, k != 0 ? 1u : 0u);
+          umma_commit(&s_ready[g]);
+          if (p.trace && blockIdx.x == 0 && ui == 0) p.trace[64 + jb * 2 + g] = clock64();
+          wcnt++;
+          if (jb == NBLK - 1) umma_commit(&q_empty[qs]);   // Q tile reusable once these MMAs retire
+        };
+        {   // rel-pos projection T_g = Q_g * Tab^T into the S region
+          wait_s_region();
+          const uint64_t bdesc = umma_desc_k128(smem_u32(sTab));
+          const uint64_t adesc = umma_desc_k128(smem_u32(sQu + g * 16384));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ss(tmem_base + g * 128, adesc + 2 * k, bdesc + 2 * k, idT, k != 0 ? 1u : 0u);
+          wcnt++;
+          umma_commit(&t_ready[g]);
         }
         if constexpr (kWindow) {
           mbar_wait(kv_fixed, ui & 1);
           tc_fence_after_sync();
         }
-        int ns[2] = {0, 0}, npv[2] = {0, 0};      // next S / PV block per group (this unit)
-        int kv_seen = 0, released = 0;
-        bool q_released = false;
-        const int gb0 = ui * NBLK;                // global-mode ring position of this unit's block 0
-        while (npv[0] < NBLK || (nact == 2 && npv[1] < NBLK)) {
-          for (int g = 0; g < nact; ++g) {
-            // ---- O += P V for the oldest pending block of this group ----
-            if (npv[g] < ns[g] && mbar_try_wait(&p_ready[g], (bcnt[g] + npv[g]) & 1)) {
-              tc_fence_after_sync();
-              const int jb = npv[g];
-              const int nkeys = (kWindow && jb == NBLK - 1) ? kLastMma : 128;
-              const uint32_t pbase = smem_u32(sP + g * 32768);
-              const uint32_t vbase = kWindow ? smem_u32(sKV + ks * SM::kKVStage + KVH + jb * 16384)
-                                             : smem_u32(sKV + ((gb0 + jb) % kAtcKVStages) * SM::kKVStage + KVH);
-              constexpr uint32_t idPV = umma_idesc_f16_bmn(128, 64);
-              const uint32_t d = tmem_base + 256 + g * 64;
-              for (int k = 0; k < nkeys / 16; ++k) {
-                const uint64_t adesc = umma_desc_k128(pbase + (k >> 2) * 16384) + 2 * (k & 3);
-                const uint64_t bdesc = umma_desc_k128(vbase + k * 2048);
-                umma_f16_ss(d, adesc, bdesc, idPV, (jb | k) != 0 ? 1u : 0u);
-              }
-              umma_commit(&pv_done[g]);
-              npv[g]++;
-              if constexpr (!kWindow) {
-                const int done = nact == 2 ? (npv[0] < npv[1] ? npv[0] : npv[1]) : npv[0];
-                while (released < done) {       // every active group finished with block `released`
-                  umma_commit(&kv_empty[(gb0 + released) % kAtcKVStages]);
-                  released++;
-                }
-              }
-            }
-            // ---- S = Q K^T for the next block of this group ----
-            if (ns[g] < NBLK) {
-              const int jb = ns[g];
-              bool ok = mbar_try_wait(&s_free[g], (wcnt[g] - 1) & 1);
-              if (ok && jb >= kv_seen) {
-                if (kWindow) {
-                  if (jb == 0 && !mbar_try_wait(&kv_full[ks], (ui / kAtcKVStages) & 1)) ok = false;
-                  else kv_seen = NBLK;            // one TMA filled the whole window
-                } else {
-                  const int gbk = gb0 + jb;
-                  if (mbar_try_wait(&kv_full[gbk % kAtcKVStages], (gbk / kAtcKVStages) & 1)) kv_seen = jb + 1;
-                  else ok = false;
-                }
-              }
-              if (ok) {
-                tc_fence_after_sync();
-                const int nkeys = (kWindow && jb == NBLK - 1) ? kLastMma : 128;
-                const uint32_t kbase = kWindow ? smem_u32(sKV + ks * SM::kKVStage + jb * 16384)
-                                               : smem_u32(sKV + ((gb0 + jb) % kAtcKVStages) * SM::kKVStage);
-                const uint32_t idS = umma_idesc_f16(128, nkeys);
-                const uint64_t adesc = umma_desc_k128(smem_u32(sQu + g * 16384));
-                const uint64_t bdesc = umma_desc_k128(kbase);
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_f16_ss(tmem_base + g * 128, adesc + 2 * k, bdesc + 2 * k, idS, k != 0 ? 1u : 0u);
-                umma_commit(&s_ready[g]);
-                ns[g]++;
-                wcnt[g]++;
-              }
-            }
+        // the two groups share each SMSP's MUFU: start group 1 half a block behind group 0 so that
+        // one group's exponentials overlap the other's TMEM loads / max / P stores
+        if (g == 1) mbar_wait(stagger, ui & 1);
+        issue_s(0);
+        for (int jb = 0; jb < NBLK; ++jb) {
+          if (jb + 1 < NBLK) issue_s(jb + 1);
+          // ---- O += P V ----
+          mbar_wait(&p_ready[g], (bcnt + jb) & 1);
+          tc_fence_after_sync();
+          const int nkeys = (kWindow && jb == NBLK - 1) ? kLastMma : 128;
+          const uint32_t pbase = smem_u32(sP + g * 32768);
+          const uint32_t vbase = kWindow ? smem_u32(sKV + ks * SM::kKVStage + KVH + jb * 16384)
+                                         : smem_u32(sKV + ((gb0 + jb) % kAtcKVStages) * SM::kKVStage + KVH);
+          const uint32_t d = tmem_base + 256 + g * 64;
+          for (int k = 0; k < nkeys / 16; ++k) {
+            const uint64_t adesc = umma_desc_k128(pbase + (k >> 2) * 16384) + 2 * (k & 3);
+            const uint64_t bdesc = umma_desc_k128(vbase + k * 2048);
+            umma_f16_ss(d, adesc, bdesc, idPV, (jb | k) != 0 ? 1u : 0u);
           }
-          if (!q_released && ns[0] == NBLK && (nact == 1 || ns[1] == NBLK)) {
-            umma_commit(&q_empty[qs]);          // Q tile may be overwritten once these MMAs retire
-            q_released = true;
-          }
+          umma_commit(&pv_done[g]);
+          if (p.trace && blockIdx.x == 0 && ui == 0) p.trace[96 + jb * 2 + g] = clock64();
+          if constexpr (!kWindow) umma_commit(&kv_empty[(gb0 + jb) % kAtcKVStages]);   // 1 of 2 arrivals
         }
         if constexpr (kWindow) umma_commit(&kv_empty[ks]);
-        for (int g = 0; g < nact; ++g) bcnt[g] += NBLK;
+        bcnt += NBLK;
       }
     }
   } else {
@@ -350,7 +345,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         // t_ready(ui) first: it is committed by the MMA warp inside unit ui, so no thread (in
         // particular none of an inactive group 1, which has nothing else to wait for) can arrive on
         // kv_fixed for a later unit before the MMA warp has consumed this unit's phase.
-        mbar_wait(t_ready, ui & 1);
+        mbar_wait(&t_ready[g], ui & 1);
         const int ks = ui % kAtcKVStages;
         uint8_t* kvs = sKV + ks * SM::kKVStage;
         mbar_wait(&kv_full[ks], (ui / kAtcKVStages) & 1);
@@ -389,7 +384,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       // rel_h[kh] = T_h[qy - kh + WIN-1] ; rel_w[kw] = T_w[qx - kw + WIN-1]  (image_encoder.py:318-322)
       float rel_h[WIN], rel_w[WIN];
       {
-        if constexpr (!kWindow) mbar_wait(t_ready, ui & 1);
+        if constexpr (!kWindow) mbar_wait(&t_ready[g], ui & 1);
         tc_fence_after_sync();
         const int sy = (kWindow && qrow >= KEYS) ? 0 : qy;
         const int sx = (kWindow && qrow >= KEYS) ? 0 : qx;
@@ -415,13 +410,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         }
       }
 
+      float2 relw2[WIN / 2];
+#pragma unroll
+      for (int i = 0; i < WIN / 2; ++i) relw2[i] = make_float2(rel_w[2 * i], rel_w[2 * i + 1]);
       float m_ref = 0.f, l_run = 0.f;
 #pragma unroll(kWindow ? NBLK : 1)
       for (int jb = 0; jb < NBLK; ++jb) {
         constexpr int kChunksLast = (kLastKeys + 31) / 32;
         const int nchunk = (kWindow && jb == NBLK - 1) ? kChunksLast : 4;
         const uint32_t par = static_cast<uint32_t>((bcnt + jb) & 1);
+        const bool tr = p.trace && blockIdx.x == 0 && warp == 4 && lane == 0 && ui == 0;
+        long long* trp = p.trace + jb * 8;
+        if (tr) trp[0] = clock64();
         mbar_wait(&s_ready[g], par);
+        if (tr) trp[1] = clock64();
         tc_fence_after_sync();
         // ---- one sweep: the whole S row into registers, then release the S buffer ----
         uint32_t sraw[128];
@@ -429,63 +431,60 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         for (int c = 0; c < 4; ++c)
           if (c < nchunk) tmem_ld_32x32_nowait(tS + c * 32, sraw + c * 32);
         tmem_ld_wait();
+        if (tr) trp[2] = clock64();
         tc_fence_before_sync();
         mbar_arrive(&s_free[g]);
-        // ---- logits (log2 domain) and block max ----
-        float y[128];
+        // ---- logits (log2 domain) and block max; packed fp32x2 math (FFMA2/FADD2) halves the issue
+        // slots of the element-wise work, which bounds this kernel together with the MUFU pipe ----
+        float2 y2[64];
         float m_blk = -INFINITY;
         float rhc[4];      // global mode: per-chunk key-row constant, folded in after the max
+        const float2 sl2 = make_float2(p.scale_log2e, p.scale_log2e);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           rhc[c] = 0.f;
           if (c < nchunk) {
+            float mq[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
             if constexpr (!kWindow) {
               // keys of chunk c of block jb: kh = jb*(128/WIN) + (c*32+i)/WIN, kw = (c*32+i) % WIN
               constexpr int NU = (32 + WIN - 1) / WIN;   // key rows spanned by a 32-key chunk (1 or 2)
-              float mc[NU], mq[NU][4];
+              float rh[NU];
 #pragma unroll
-              for (int uu = 0; uu < NU; ++uu)
-                mq[uu][0] = mq[uu][1] = mq[uu][2] = mq[uu][3] = -INFINITY;
+              for (int uu = 0; uu < NU; ++uu) rh[uu] = rel_h[jb * (128 / WIN) + (c * 32) / WIN + uu];
+              rhc[c] = rh[0];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const float v = fmaf(__uint_as_float(sraw[c * 32 + i]), p.scale_log2e,
-                                     rel_w[(c * 32 + i) % WIN]);
-                y[c * 32 + i] = v;
-                mq[i / WIN][i & 3] = fmaxf(mq[i / WIN][i & 3], v);
-              }
-#pragma unroll
-              for (int uu = 0; uu < NU; ++uu)
-                mc[uu] = fmaxf(fmaxf(mq[uu][0], mq[uu][1]), fmaxf(mq[uu][2], mq[uu][3]));
-              float best = -INFINITY;
-#pragma unroll
-              for (int uu = 0; uu < NU; ++uu) {
-                const float rh = rel_h[jb * (128 / WIN) + (c * 32) / WIN + uu];
-                if (uu == 0) rhc[c] = rh;
-                best = fmaxf(best, mc[uu] + rh);
-                if (uu > 0) {                      // WIN = 16: second key row of the chunk: fold now
-#pragma unroll
-                  for (int i = 0; i < 32; ++i)
-                    if (i / WIN == uu) y[c * 32 + i] += rh - rhc[c];
+              for (int j = 0; j < 16; ++j) {
+                const int i = 2 * j;
+                float2 v = __ffma2_rn(make_float2(__uint_as_float(sraw[c * 32 + i]),
+                                                  __uint_as_float(sraw[c * 32 + i + 1])),
+                                      sl2, relw2[((c * 32 + i) % WIN) / 2]);
+                if (NU > 1 && i / WIN > 0) {             // WIN = 16: second key row of the chunk
+                  const float d = rh[NU - 1] - rh[0];
+                  v = __fadd2_rn(v, make_float2(d, d));
                 }
+                y2[c * 16 + j] = v;
+                mq[j & 3] = fmaxf(mq[j & 3], fmaxf(v.x, v.y));
               }
-              m_blk = fmaxf(m_blk, best);
+              m_blk = fmaxf(m_blk, fmaxf(fmaxf(mq[0], mq[1]), fmaxf(mq[2], mq[3])) + rh[0]);
             } else {
 #pragma unroll
-              float mq[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const int key = jb * 128 + c * 32 + i;
-                float v = -INFINITY;
-                if (key < KEYS)
-                  v = fmaf(__uint_as_float(sraw[c * 32 + i]), p.scale_log2e,
-                           rel_h[key / WIN] + rel_w[key % WIN]);
-                y[c * 32 + i] = v;
-                mq[i & 3] = fmaxf(mq[i & 3], v);
+              for (int j = 0; j < 16; ++j) {
+                const int key = jb * 128 + c * 32 + 2 * j;         // even; KEYS and WIN are even
+                float2 v = make_float2(-INFINITY, -INFINITY);
+                if (key < KEYS) {
+                  const float rh = rel_h[key / WIN];
+                  v = __ffma2_rn(make_float2(__uint_as_float(sraw[c * 32 + 2 * j]),
+                                             __uint_as_float(sraw[c * 32 + 2 * j + 1])),
+                                 sl2, __fadd2_rn(make_float2(rh, rh), relw2[(key % WIN) / 2]));
+                }
+                y2[c * 16 + j] = v;
+                mq[j & 3] = fmaxf(mq[j & 3], fmaxf(v.x, v.y));
               }
               m_blk = fmaxf(m_blk, fmaxf(fmaxf(mq[0], mq[1]), fmaxf(mq[2], mq[3])));
             }
           }
         }
+        if (tr) trp[3] = clock64() + static_cast<long long>(m_blk > 1e30f);
         // ---- lazy reference max: rescale O / l only when the row max grew by more than 2^8 ----
         bool pv_waited = false;
         if (jb == 0) {
@@ -511,31 +510,36 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             tmem_st_wait();
           }
         }
-        // ---- p = 2^(y - m_ref) packed to fp16 in registers, row sum (4 partial sums) ----
+        // ---- p = 2^(y - m_ref) packed to fp16 in registers, row sum (packed partial sums) ----
         uint32_t pk[64];
-        float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
+        float2 lsa = make_float2(0.f, 0.f), lsb = make_float2(0.f, 0.f);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           if (c < nchunk) {
             const float sub = rhc[c] - m_ref;
+            const float2 sub2 = make_float2(sub, sub);
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float p0 = ex2_approx(y[c * 32 + i + 0] + sub);
-              const float p1 = ex2_approx(y[c * 32 + i + 1] + sub);
-              const float p2 = ex2_approx(y[c * 32 + i + 2] + sub);
-              const float p3 = ex2_poly3(y[c * 32 + i + 3] + sub);   // FMA-pipe exp (1 in 4)
-              ls0 += p0; ls1 += p1; ls2 += p2; ls3 += p3;
-              pk[c * 16 + i / 2] = pack_half2(p0, p1);
-              pk[c * 16 + i / 2 + 1] = pack_half2(p2, p3);
+            for (int j = 0; j < 16; j += 2) {
+              const float2 a0 = __fadd2_rn(y2[c * 16 + j], sub2);
+              const float2 a1 = __fadd2_rn(y2[c * 16 + j + 1], sub2);
+              const float2 p0 = make_float2(ex2_approx(a0.x), ex2_approx(a0.y));
+              const float2 p1 = make_float2(ex2_approx(a1.x), ex2_poly3(a1.y));   // 1 in 4 on the FMA pipe
+              lsa = __fadd2_rn(lsa, p0);
+              lsb = __fadd2_rn(lsb, p1);
+              pk[c * 16 + j] = pack_half2(p0.x, p0.y);
+              pk[c * 16 + j + 1] = pack_half2(p1.x, p1.y);
             }
+            if (g == 0 && jb == 0 && c == 1) mbar_arrive(stagger);   // ~half a block into the unit
           }
         }
-        l_run += (ls0 + ls1) + (ls2 + ls3);
+        l_run += (lsa.x + lsa.y) + (lsb.x + lsb.y);
+        if (tr) trp[4] = clock64() + static_cast<long long>(l_run > 1e30f);
         // ---- P -> smem (swizzled) once PV(jb-1) has finished reading the buffer ----
         if (jb > 0 && !pv_waited) {
           mbar_wait(&pv_done[g], par ^ 1u);
           tc_fence_after_sync();
         }
+        if (tr) trp[5] = clock64();
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           if (c < nchunk) {
@@ -549,9 +553,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             }
           }
         }
+        if (tr) trp[6] = clock64();
         tc_fence_before_sync();
         fence_proxy_async_smem();
         mbar_arrive(&p_ready[g]);
+        if (tr) trp[7] = clock64();
       }
 
       // ---- epilogue of the unit: O / l -> global ----

@@ -94,6 +94,25 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return fmaf(-a, e, fmaxf(x, 0.0f));
 }
 
+// Two elements per instruction on the packed fp32x2 pipe (FFMA2): the polynomial is evaluated in
+// t = -min(|x|, 5.6) (odd coefficients negated) so that no packed negation is needed.  Same
+// coefficients, same rounding per lane as gelu_erf_fast -> bit-identical results.
+__device__ __forceinline__ float2 gelu_erf_fast2(float2 x) {
+  const float2 na = make_float2(fminf(x.x, -x.x), fminf(x.y, -x.y));
+  const float2 t = make_float2(fmaxf(na.x, -5.6f), fmaxf(na.y, -5.6f));
+  float2 l = __ffma2_rn(make_float2(3.45301887136884e-05f, 3.45301887136884e-05f), t,
+                        make_float2(0.0007803441258147359f, 0.0007803441258147359f));
+  l = __ffma2_rn(l, t, make_float2(0.008112940937280655f, 0.008112940937280655f));
+  l = __ffma2_rn(l, t, make_float2(0.05345592275261879f, 0.05345592275261879f));
+  l = __ffma2_rn(l, t, make_float2(-0.45874229073524475f, -0.45874229073524475f));
+  l = __ffma2_rn(l, t, make_float2(1.1512099504470825f, 1.1512099504470825f));
+  l = __ffma2_rn(l, t, make_float2(-0.999992311000824f, -0.999992311000824f));
+  float2 e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(l.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(l.y));
+  return __ffma2_rn(na, e, make_float2(fmaxf(x.x, 0.0f), fmaxf(x.y, 0.0f)));
+}
+
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
@@ -134,6 +153,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe (mbarrier.try_wait may suspend the thread for a system-dependent time before it
+// returns false, which is poison for a loop that polls several barriers)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
@@ -153,6 +187,32 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)),
       "r"(c0), "r"(c1)
       : "memory");
+}
+// TMA store (shared::cta -> global) through a bulk async-group; the smem source may be reused once
+// cp.async.bulk.wait_group.read has retired the group.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* smem_src, int32_t c0,
+                                             int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+// TMA reduce-add (fp32): global[tile] += smem[tile], performed at L2.
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, const void* smem_src,
+                                                  int32_t c0, int32_t c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_group() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar,
                                             int32_t c0, int32_t c1, int32_t c2) {

@@ -39,7 +39,7 @@ constexpr int kGemmScratchFloats = 32 * 36;   // per epilogue warp: 32x32 fp32 b
 
 
 __device__ __forceinline__ float apply_act(float x, int act) {
-  if (act == ACT_GELU) return gelu_erf_fast(x);
+  if (act == ACT_GELU || act == ACT_GELU_SCALAR) return gelu_erf_fast(x);
   if (act == ACT_RELU) return fmaxf(x, 0.0f);
   if (act == ACT_SIGMOID) return sigmoidf_(x);
   return x;
@@ -97,18 +97,38 @@ struct EpiF16 {
   };
   static __device__ __forceinline__ void run(const Params& p, int m0, int M, int n_base, int n_cols,
                                              const TmemRow& row, float* scratch, int lane) {
+    if (p.act >= ACT_PROBE_SKIP) {          // timing ablations (tools/gemm_probe.py), never a result
+      if (p.act == ACT_PROBE_SKIP) return;
+      if (p.act == ACT_PROBE_TMEM) {
+        float acc = 0.f;
+        for (int c = 0; c < (n_cols >> 5); ++c) {
+          float v[32];
+          row.load(c, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc += v[i];
+        }
+        if (acc == 1234.5678f) p.out[0] = __float2half(acc);
+        return;
+      }
+    }
+    const bool probe_nostore = p.act == ACT_PROBE_NOSTORE;
+    const int act = probe_nostore ? ACT_GELU : p.act;
     epi_stream_chunks(n_cols, row, scratch, lane, [&](int c, int rr, int cc, float4 x) {
       const int n = n_base + c * 32 + cc;
       if (p.bias) {
         const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
         x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
       }
-      if (p.act != ACT_NONE) {
-        x.x = apply_act(x.x, p.act); x.y = apply_act(x.y, p.act);
-        x.z = apply_act(x.z, p.act); x.w = apply_act(x.w, p.act);
+      if (act == ACT_GELU) {
+        const float2 g0 = gelu_erf_fast2(make_float2(x.x, x.y));
+        const float2 g1 = gelu_erf_fast2(make_float2(x.z, x.w));
+        x = make_float4(g0.x, g0.y, g1.x, g1.y);
+      } else if (act != ACT_NONE) {
+        x.x = apply_act(x.x, act); x.y = apply_act(x.y, act);
+        x.z = apply_act(x.z, act); x.w = apply_act(x.w, act);
       }
       const int m = m0 + rr;
-      if (m < M) {
+      if (m < M && !(probe_nostore && x.x != 1234.5678f)) {
         uint2 u;
         u.x = pack_half2(x.x, x.y);
         u.y = pack_half2(x.z, x.w);

@@ -9,27 +9,68 @@
 //   leader    : warp 1 lane 0 issues tcgen05.mma.cta_group::2 and multicasts the commits
 #pragma once
 
+#include <type_traits>
+
 #include "gemm_tc.cuh"
 
 namespace srb {
 
 constexpr int kGemm2Stages = 5;
 
+constexpr int kGemm2OutBytes = 32 * 64 * 2;     // one 32-row x 64-column fp16 block (128 B rows)
+
 struct Gemm2Smem {
   static constexpr int kABytes = 128 * kGemmBK * 2;
   static constexpr int kStageBytes = 2 * kABytes;                    // A half + B half
-  static constexpr int kBarOffset = kGemm2Stages * kStageBytes;
-  static constexpr int kScratchOffset = kBarOffset + 256;
-  static constexpr int kTotal = kScratchOffset + kGemmEpiWarps * kGemmScratchFloats * 4 + 1024;
+  static constexpr int kOutOffset = kGemm2Stages * kStageBytes;      // 1024-aligned
+  static constexpr int kBarOffset = kOutOffset + kGemmEpiWarps * 2 * kGemm2OutBytes;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;
 };
+
+// fp16 epilogue of the 2-CTA kernel: out16 = act(acc + bias), one accumulator row per lane.  The
+// 32 x 64 block is laid out in smem exactly as a 128B-swizzled TMA box (16 B piece j of row r at
+// r*128 + ((j ^ (r & 7)) << 4): conflict-free 16 B stores) and leaves through a TMA store, so the
+// epilogue costs 2 KB of smem writes + 2 KB of TMA reads per 32 x 32 accumulator block instead of
+// the 8 KB of the transposing epilogue -- shared-memory bandwidth is what the K = 768 GEMMs of the
+// encoder are short of (tools/gemm_probe.py: main loop alone 1.55 PFLOP/s).
+__device__ __forceinline__ void epi_f16_pack_chunk(const float (&v)[32], const float* __restrict__ bias_n,
+                                                   int act, uint8_t* row_base, uint32_t piece0,
+                                                   uint32_t sw) {
+  const float4* bp = reinterpret_cast<const float4*>(bias_n);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 x[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bias_n) bb = __ldg(bp + 2 * i + h);
+      x[2 * h] = __fadd2_rn(make_float2(v[8 * i + 4 * h], v[8 * i + 4 * h + 1]), make_float2(bb.x, bb.y));
+      x[2 * h + 1] = __fadd2_rn(make_float2(v[8 * i + 4 * h + 2], v[8 * i + 4 * h + 3]), make_float2(bb.z, bb.w));
+    }
+    if (act == ACT_GELU) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) x[k] = gelu_erf_fast2(x[k]);
+    } else if (act != ACT_NONE) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) x[k] = make_float2(apply_act(x[k].x, act), apply_act(x[k].y, act));
+    }
+    uint4 u;
+    u.x = pack_half2(x[0].x, x[0].y);
+    u.y = pack_half2(x[1].x, x[1].y);
+    u.z = pack_half2(x[2].x, x[2].y);
+    u.w = pack_half2(x[3].x, x[3].y);
+    *reinterpret_cast<uint4*>(row_base + (((piece0 + static_cast<uint32_t>(i)) ^ sw) << 4)) = u;
+  }
+}
 
 template <class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                int M, int N, int K, typename Epi::Params ep) {
+                const __grid_constant__ CUtensorMap tmO, int M, int N, int K, typename Epi::Params ep) {
   using SM = Gemm2Smem;
   constexpr int STAGES = kGemm2Stages;
   constexpr int BN = 256;
+  constexpr bool kTmaOut = std::is_same<Epi, EpiF16>::value;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -55,6 +96,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (kTmaOut) tma_prefetch_desc(&tmO);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 2);      // leader: arrive.expect_tx + the peer's remote arrive
       mbar_init(&empty_bar[s], 1);     // multicast commit from the leader's MMA thread
@@ -125,8 +167,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     if (Epi::kSplitCols || half == 0) {
-      float* scratch = reinterpret_cast<float*>(smem + SM::kScratchOffset) +
-                       (warp - 2) * kGemmScratchFloats;
+      uint8_t* obuf = smem + SM::kOutOffset + (warp - 2) * (2 * kGemm2OutBytes);
+      const uint32_t sw = static_cast<uint32_t>(lane & 7);
+      int gs = 0;                         // 64-column blocks stored so far (smem double buffer)
       int as = 0;
       uint32_t aphase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
@@ -138,7 +181,32 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (Epi::kSplitCols) { col0 = half * (BN / 2); n_cols = BN / 2; }
         TmemRow row{tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                     static_cast<uint32_t>(as * BN + col0)};
-        Epi::run(ep, m0, M, n_blk * BN + col0, n_cols, row, scratch, lane);
+        if constexpr (kTmaOut) {
+          if (ep.act != ACT_PROBE_SKIP) {
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h, ++gs) {
+              uint8_t* buf = obuf + (gs & 1) * kGemm2OutBytes;
+              if (lane == 0) bulk_wait_group_read<1>();     // the store two blocks ago has left buf
+              __syncwarp();
+              const int n0 = n_blk * BN + col0 + h * 64;
+#pragma unroll
+              for (int cc = 0; cc < 2; ++cc) {
+                float v[32];
+                row.load(2 * h + cc, v);
+                epi_f16_pack_chunk(v, ep.bias ? ep.bias + n0 + cc * 32 : nullptr, ep.act,
+                                   buf + lane * 128, static_cast<uint32_t>(cc * 4), sw);
+              }
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tmO, buf, n0, m0);
+                bulk_commit_group();
+              }
+            }
+          }
+        } else {
+          Epi::run(ep, m0, M, n_blk * BN + col0, n_cols, row, nullptr, lane);
+        }
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) {
@@ -148,6 +216,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         as ^= 1;
         if (as == 0) aphase ^= 1u;
       }
+      if (kTmaOut && lane == 0) bulk_wait_group<0>();
     }
   }
 
@@ -162,9 +231,13 @@ int launch_gemm_tc2(const __half* A, int lda, const __half* W, int ldw, int M, i
   using SM = Gemm2Smem;
   SRB_REQUIRE(N % 256 == 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm2: bad shape N=%d K=%d",
               N, K);
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmO;
   if (int rc = make_tmap_f16_2d(&tmA, A, M, K, lda, 128)) return rc;
   if (int rc = make_tmap_f16_2d(&tmB, W, N, K, ldw, 128)) return rc;
+  tmO = tmA;
+  if constexpr (std::is_same<Epi, EpiF16>::value) {
+    if (int rc = make_tmap_f16_2d(&tmO, ep.out, M, N, ep.ldo, 32)) return rc;
+  }
   auto kern = gemm_tc2_kernel<Epi>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -174,7 +247,7 @@ int launch_gemm_tc2(const __half* A, int lda, const __half* W, int ldw, int M, i
   const int num_tiles = ((M + 255) / 256) * (N / 256);
   const int max_clusters = device_sm_count() / 2;
   const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
-  kern<<<2 * clusters, kGemmThreads, SM::kTotal, stream>>>(tmA, tmB, M, N, K, ep);
+  kern<<<2 * clusters, kGemmThreads, SM::kTotal, stream>>>(tmA, tmB, tmO, M, N, K, ep);
   SRB_CUDA_OK(cudaGetLastError());
   note_launch(1);
   return 0;

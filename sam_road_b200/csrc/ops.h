@@ -8,7 +8,14 @@
 
 namespace srb {
 
-enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_SIGMOID = 3 };
+enum Act : int {
+  ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_SIGMOID = 3,
+  ACT_GELU_SCALAR = 4,         // same function, one element per instruction (A/B timing only)
+  // tools/gemm_probe.py only: epilogue ablations that do NOT produce the result
+  ACT_PROBE_SKIP = 100,        // release the accumulator untouched (main-loop ceiling)
+  ACT_PROBE_TMEM = 101,        // TMEM loads only
+  ACT_PROBE_NOSTORE = 102      // full GELU epilogue without the global stores
+};
 
 void set_last_error(const char* fmt, ...);
 const char* get_last_error();
@@ -30,7 +37,7 @@ int gemm_dec_final(const __half* A, int lda, const __half* W, int ldw, int M, in
                    const float* bias3, const float* w4, const float* bias4, int s, int P,
                    float* scores, float* logits, cudaStream_t st);
 // plain SIMT fp32-accumulate GEMM used only by the on-device unit tests as an independent checker
-void gemm_disable_2cta(bool off);   // test hook: force the 1-CTA kernels
+void gemm_disable_2cta(int mode);   // test hook: bit 0 forces the 1-CTA kernels, bit 1 the register-path fp32 epilogue
 int gemm_ref_simt(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K,
                   float* out, int ldo, cudaStream_t st);
 
@@ -59,6 +66,7 @@ int pack_rel_table(const float* rel_h, const float* rel_w, int win, int hd, __ha
                    cudaStream_t st);
 // force the SIMT v1 attention kernel (tests use it as the independent on-device checker)
 void attention_force_simt(bool on);
+void attention_set_trace(long long* device_buffer_128);   // debug: per-phase clock64 stamps of CTA 0
 
 // ---- TopoNet pieces (toponet.cu) -----------------------------------------------------------------------------
 // points dtype: 0 = float32, 1 = int64, 2 = int32 ; pairs dtype: 1 = int64, 2 = int32

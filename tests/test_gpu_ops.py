@@ -107,6 +107,36 @@ def test_gemm_f32_resid_pos(M, N, K):
     assert (out2 - A.float() @ W.float().t()).abs().max().item() < 2e-4 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("M,N,K", [(65536, 768, 768), (20001, 768, 3072), (9999, 1024, 512)])
+def test_gemm_f32_inplace_shortcut_tma(M, N, K):
+    """x += A.W^T + b in the 2-CTA kernel (gemm_tc2r.cuh).  Default: the shortcut add is a TMA
+    reduce-add in L2 (x + (acc + b)); hook variant 4 streams the shortcut through smem and must agree
+    bit for bit with the register-path epilogue (2) and the 1-CTA kernel (1)."""
+    lib = _lib.load()
+    A = _rand16((M, K), 1.0, 31)
+    W = _rand16((N, K), 1.0 / math.sqrt(K), 32)
+    bias = torch.randn(N, device=DEV)
+    resid = torch.randn(M, N, device=DEV) * 3
+    ref = resid + bias
+    for m0 in range(0, M, 16384):     # chunked: keeps the fp32 reference product small
+        ref[m0:m0 + 16384] += A[m0:m0 + 16384].float() @ W.float().t()
+    outs = []
+    for mode in (0, 4, 2, 1):
+        lib.samroad_debug_disable_2cta_gemm(mode)
+        out = resid.clone()
+        _lib.check(lib.samroad_op_gemm_f32(A.data_ptr(), K, W.data_ptr(), K, M, N, K, bias.data_ptr(),
+                                           out.data_ptr(), None, 0, out.data_ptr(), N, _st()),
+                   "gemm_f32 in place")
+        torch.cuda.synchronize()
+        outs.append(out)
+    lib.samroad_debug_disable_2cta_gemm(0)
+    tol = 2e-4 * max(1.0, ref.abs().max().item())
+    assert (outs[0] - ref).abs().max().item() < tol
+    assert (outs[1] - ref).abs().max().item() < tol
+    assert (outs[0] - outs[1]).abs().max().item() < 4e-6 * max(1.0, ref.abs().max().item())
+    assert torch.equal(outs[1], outs[2]) and torch.equal(outs[1], outs[3])
+
+
 @pytest.mark.parametrize("M,N,K,group,act", [(1024, 256, 768, 256, 0), (1024, 512, 256, 128, 1),
                                              (333, 128, 128, 128, 0), (20000, 512, 256, 128, 1),
                                              (2048, 256, 2304, 256, 0)])
