@@ -144,15 +144,17 @@ int samroad_op_attention(const void* qkv16, const float* qkv_bias, const float* 
                          const float* rel_w, int B, int s, int win, int heads, int head_dim,
                          void* out16, void* stream);
 
-/* Test hook: route samroad_op_attention / the encoder through the fp32 SIMT attention kernel (the
- * independent on-device checker of the tcgen05 kernel).  Not for production use. */
+/* Test hook (bit mask): bit 0 routes samroad_op_attention / the encoder through the fp32 SIMT
+ * attention kernel (the independent on-device checker of the tcgen05 kernel); bit 1 selects the
+ * tcgen05 variant that evaluates 1 in 4 softmax exponentials as a polynomial on the FMA pipe (A/B
+ * timing, tools/att_trace.py).  Not for production use. */
 void samroad_debug_force_simt_attention(int on);
 /* Test hook (bit mask): bit 0 routes every GEMM through the 1-CTA kernels (the 2-CTA cta_group::2
  * kernel is then checked against them); bit 1 routes the in-place fp32 shortcut GEMMs through the
  * register-path epilogue instead of the TMA one; bit 2 selects the TMA load+store variant of that
  * epilogue (bit-identical to the register path) instead of the default TMA reduce-add. */
 void samroad_debug_disable_2cta_gemm(int off);
-/* Debug hook: device buffer of 128 int64 receiving clock64 stamps of CTA 0's first work unit in the
+/* Debug hook: device buffer of 256 int64 receiving clock64 stamps of CTA 0's first work unit in the
  * tcgen05 attention kernel (softmax warp phases, MMA issue times); NULL disables. */
 void samroad_debug_attention_trace(void* dev_buf);
 

@@ -224,9 +224,11 @@ int pack_rel_table(const float* rel_h, const float* rel_w, int win, int hd, __ha
 }
 
 static bool g_force_simt = false;
+static bool g_no_stagger = false;
+static bool g_poly = false;         // A/B hook: 1 in 4 softmax exponentials as a polynomial on the FMA pipe
 static long long* g_att_trace = nullptr;
 void attention_set_trace(long long* p) { g_att_trace = p; }
-void attention_force_simt(bool on) { g_force_simt = on; }
+void attention_force_simt(int mode) { g_force_simt = (mode & 1) != 0; g_poly = (mode & 2) != 0; g_no_stagger = (mode & 4) != 0; }
 
 template <bool kWindow, int WIN>
 static int launch_attention_tc(const __half* qkv, const float* qkv_bias, const __half* tab, int B,
@@ -247,11 +249,13 @@ static int launch_attention_tc(const __half* qkv, const float* qkv_bias, const _
   }
   const int rows = rel_table_rows(WIN);
   if (int rc = make_tmap_f16_2d(&tmTab, tab, rows, 64, 64, rows)) return rc;
-  auto kern = attention_tc_kernel<kWindow, WIN>;
+  auto kern = g_poly ? attention_tc_kernel<kWindow, WIN, true> : attention_tc_kernel<kWindow, WIN, false>;
   static bool attr_set = false;
   if (!attr_set) {
-    SRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     AtcSmem<kWindow>::kBytes));
+    SRB_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<kWindow, WIN, false>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, AtcSmem<kWindow>::kBytes));
+    SRB_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<kWindow, WIN, true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, AtcSmem<kWindow>::kBytes));
     attr_set = true;
   }
   AtcParams p;
@@ -261,6 +265,7 @@ static int launch_attention_tc(const __half* qkv, const float* qkv_bias, const _
   const int units = kWindow ? B * p.nwin * p.nwin * heads : B * (T / 256) * heads;
   p.num_units = units;
   p.trace = g_att_trace;
+  p.no_stagger = g_no_stagger ? 1 : 0;
   const int grid = units < device_sm_count() ? units : device_sm_count();   // persistent CTAs
   kern<<<grid, kAtcThreads, AtcSmem<kWindow>::kBytes, st>>>(tmQKV, tmTab, p);
   SRB_CUDA_OK(cudaGetLastError());

@@ -62,7 +62,8 @@ struct AtcParams {
   int nwin;                // windows per side (window mode)
   int num_units;
   float scale_log2e;       // head_dim^-0.5 * log2(e)
-  long long* trace;        // debug: clock64 stamps of CTA 0 (softmax warp 4: 8 per block; MMA thread), or null
+  int no_stagger;          // A/B hook: do not delay group 1 by half a block
+  long long* trace;        // debug: 256 clock64 stamps of CTA 0 (softmax warp 4: 8 per block; MMA threads; unit phases), or null
 };
 
 struct AtcUnit {
@@ -96,7 +97,7 @@ __device__ __forceinline__ bool atc_group1_active(const AtcUnit& un, const AtcPa
   return true;
 }
 
-template <bool kWindow, int WIN>
+template <bool kWindow, int WIN, bool kPoly>
 __global__ void __launch_bounds__(kAtcThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmTab,
                     AtcParams p) {
@@ -134,6 +135,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
   uint64_t* t_ready = bars + 21;                // [2]
   uint64_t* stagger = bars + 23;                // group 0 -> group 1 issuer: half-block phase offset
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  uint64_t* kv_seen = bars + 25;                // both issuers are past kv_fixed(ui) (paces warp 3)
+  uint64_t* t_free = bars + 26;                 // [2] rel-pos projection T_g gathered (kSepT)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -144,8 +147,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     tma_prefetch_desc(&tmTab);
     mbar_init(tab_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 2); mbar_init(&t_ready[i], 1); }
-    mbar_init(kv_fixed, 256);
+    mbar_init(kv_fixed, 1);
+    mbar_init(kv_seen, 2);
     mbar_init(stagger, 128);
+    for (int i = 0; i < 2; ++i) mbar_init(&t_free[i], 128);
     for (int i = 0; i < kAtcKVStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 2); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_ready[i], 1);
@@ -172,7 +177,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384)
+  // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384); a 64-row rel-pos table gets its
+  // own T0 [384,448) T1 [448,512), so the projection of the next unit and its first QK^T no longer
+  // queue behind the gather (a 128-row table, global 32x32, shares the S region)
+  constexpr bool kSepT = NTAB == 64;
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -224,6 +232,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       mbar_wait(tab_full, 0);
       int ui = 0;
       int wcnt = 0;      // writes (T or S) issued into this group's S region so far
+      int tcnt = 0;      // rel-pos projections issued into this group's own T region (kSepT)
       int bcnt = 0;      // blocks completed by this group in earlier units
       constexpr uint32_t idT = umma_idesc_f16(128, NTAB);
       constexpr uint32_t idPV = umma_idesc_f16_bmn(128, 64);
@@ -238,7 +247,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         if (!active) {     // nothing to compute, but keep the 2-arrival barriers and the pacing moving
           mbar_arrive(&t_ready[g]);
           mbar_arrive(&q_empty[qs]);
-          if constexpr (kWindow) mbar_arrive(&kv_empty[ks]);
+          if constexpr (kWindow) {
+            mbar_wait(kv_fixed, ui & 1);
+            mbar_arrive(kv_seen);
+            mbar_arrive(&kv_empty[ks]);
+          }
           continue;
         }
         tc_fence_after_sync();
@@ -271,23 +284,33 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
           wcnt++;
           if (jb == NBLK - 1) umma_commit(&q_empty[qs]);   // Q tile reusable once these MMAs retire
         };
-        {   // rel-pos projection T_g = Q_g * Tab^T into the S region
-          wait_s_region();
+        {   // rel-pos projection T_g = Q_g * Tab^T (own TMEM region, or the S region)
+          if constexpr (kSepT) {
+            if (tcnt > 0) {
+              mbar_wait(&t_free[g], (tcnt - 1) & 1);
+              tc_fence_after_sync();
+            }
+          } else {
+            wait_s_region();
+          }
           const uint64_t bdesc = umma_desc_k128(smem_u32(sTab));
           const uint64_t adesc = umma_desc_k128(smem_u32(sQu + g * 16384));
+          const uint32_t tT = kSepT ? tmem_base + 384 + g * 64 : tmem_base + g * 128;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_f16_ss(tmem_base + g * 128, adesc + 2 * k, bdesc + 2 * k, idT, k != 0 ? 1u : 0u);
-          wcnt++;
+            umma_f16_ss(tT, adesc + 2 * k, bdesc + 2 * k, idT, k != 0 ? 1u : 0u);
+          if constexpr (kSepT) tcnt++; else wcnt++;
           umma_commit(&t_ready[g]);
         }
         if constexpr (kWindow) {
           mbar_wait(kv_fixed, ui & 1);
+          mbar_arrive(kv_seen);
           tc_fence_after_sync();
         }
         // the two groups share each SMSP's MUFU: start group 1 half a block behind group 0 so that
-        // one group's exponentials overlap the other's TMEM loads / max / P stores
-        if (g == 1) mbar_wait(stagger, ui & 1);
+        // one group's exponentials overlap the other's TMEM loads / max / P stores (8-block global
+        // units only; with the 2-block window units the delay costs more than it gains)
+        if (g == 1 && !kWindow && !p.no_stagger) mbar_wait(stagger, ui & 1);
         issue_s(0);
         for (int jb = 0; jb < NBLK; ++jb) {
           if (jb + 1 < NBLK) issue_s(jb + 1);
@@ -312,6 +335,48 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         bcnt += NBLK;
       }
     }
+    else if (warp == 3) {
+      // =========================== window pad fix-up (warp 3) ===========================
+      // pad tokens of the window: k = b_k, v = b_v (fp16) written into the swizzled tiles once the
+      // K/V TMA has landed (it zero-fills them); then the tiles are handed to the MMA issuers.  K/V
+      // is double-buffered across units, so this runs a unit ahead of the softmax groups.
+      if constexpr (kWindow) {
+        int ui = 0;
+        for (int u = blockIdx.x; u < p.num_units; u += gridDim.x, ++ui) {
+          const AtcUnit un = atc_decode<kWindow, WIN>(u, p);
+          const int ry = min(WIN, p.s - un.wy * WIN), rx = min(WIN, p.s - un.wx * WIN);
+          const int ks = ui % kAtcKVStages;
+          uint8_t* kvs = sKV + ks * SM::kKVStage;
+          mbar_wait(&kv_full[ks], (ui / kAtcKVStages) & 1);
+          if (ry < WIN || rx < WIN) {
+            const float* bk = p.qkv_bias + p.D + un.head * 64;
+            const float* bv = p.qkv_bias + 2 * p.D + un.head * 64;
+            // lane = 16 B piece (8 channels) x {K, V} x 2 row phases; the bias piece is converted once
+            const int c = lane & 7;
+            const bool isv = (lane >> 3) & 1;
+            const float* bp = (isv ? bv : bk) + c * 8;
+            uint4 ub;
+            ub.x = pack_half2(__ldg(bp + 0), __ldg(bp + 1));
+            ub.y = pack_half2(__ldg(bp + 2), __ldg(bp + 3));
+            ub.z = pack_half2(__ldg(bp + 4), __ldg(bp + 5));
+            ub.w = pack_half2(__ldg(bp + 6), __ldg(bp + 7));
+            uint8_t* dstbase = kvs + (isv ? KVH : 0);
+            for (int r = lane >> 4; r < KEYS; r += 2) {
+              if (r / WIN >= ry || r % WIN >= rx)
+                *reinterpret_cast<uint4*>(dstbase + r * 128 + ((c ^ (r & 7)) << 4)) = ub;
+            }
+            fence_proxy_async_smem();
+          }
+          __syncwarp();
+          if (lane == 0) {
+            // never more than one kv_fixed phase ahead of the issuers' waits
+            if (ui > 0) mbar_wait(kv_seen, (ui - 1) & 1);
+            mbar_arrive(kv_fixed);
+          }
+          __syncwarp();
+        }
+      }
+    }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     // =========================== softmax groups ===========================
@@ -322,6 +387,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     const uint32_t tlane = static_cast<uint32_t>(quarter * 32) << 16;
     const uint32_t tS = tmem_base + tlane + g * 128;
     const uint32_t tO = tmem_base + tlane + 256 + g * 64;
+    const uint32_t tT = tmem_base + tlane + 384 + g * 64;      // kSepT only
     uint8_t* myP = sP + g * 32768 + row * 128;
     float* scratch = reinterpret_cast<float*>(sP + g * 32768);   // [HALF][128] gather scratch
     const int sw = row & 7;
@@ -330,6 +396,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     int ui = 0;
 
     for (int u = blockIdx.x; u < p.num_units; u += gridDim.x, ++ui) {
+      if (p.trace && blockIdx.x == 0 && warp == 4 && lane == 0 && ui < 8) p.trace[112 + ui] = clock64();
       const AtcUnit un = atc_decode<kWindow, WIN>(u, p);
       const bool active = g == 0 || atc_group1_active<kWindow, WIN>(un, p);
       int qy, qx, ry = WIN, rx = WIN;
@@ -340,37 +407,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         ry = min(WIN, p.s - un.wy * WIN); rx = min(WIN, p.s - un.wx * WIN);
         q_real = qrow < KEYS && qy < ry && qx < rx;
         out_tok = static_cast<size_t>(un.b) * T + (un.wy * WIN + qy) * p.s + (un.wx * WIN + qx);
-        // pad tokens of the window: k = b_k, v = b_v (fp16) written into the swizzled tiles once the
-        // K/V TMA has landed (it zero-fills them); then hand the tiles to the MMA warp.
-        // t_ready(ui) first: it is committed by the MMA warp inside unit ui, so no thread (in
-        // particular none of an inactive group 1, which has nothing else to wait for) can arrive on
-        // kv_fixed for a later unit before the MMA warp has consumed this unit's phase.
+        // every thread, also of an inactive group 1 (which has nothing else to wait for), consumes
+        // this unit's t_ready phase: nobody can run a phase ahead of the barrier parities
         mbar_wait(&t_ready[g], ui & 1);
-        const int ks = ui % kAtcKVStages;
-        uint8_t* kvs = sKV + ks * SM::kKVStage;
-        mbar_wait(&kv_full[ks], (ui / kAtcKVStages) & 1);
-        const int r = (warp - 4) * 32 + lane;      // 0..255 : one key row per thread
-        if (r < KEYS && (r / WIN >= ry || r % WIN >= rx)) {
-          const float* bk = p.qkv_bias + p.D + un.head * 64;
-          const float* bv = p.qkv_bias + 2 * p.D + un.head * 64;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            uint4 uk, uv;
-            uk.x = pack_half2(__ldg(bk + c * 8 + 0), __ldg(bk + c * 8 + 1));
-            uk.y = pack_half2(__ldg(bk + c * 8 + 2), __ldg(bk + c * 8 + 3));
-            uk.z = pack_half2(__ldg(bk + c * 8 + 4), __ldg(bk + c * 8 + 5));
-            uk.w = pack_half2(__ldg(bk + c * 8 + 6), __ldg(bk + c * 8 + 7));
-            uv.x = pack_half2(__ldg(bv + c * 8 + 0), __ldg(bv + c * 8 + 1));
-            uv.y = pack_half2(__ldg(bv + c * 8 + 2), __ldg(bv + c * 8 + 3));
-            uv.z = pack_half2(__ldg(bv + c * 8 + 4), __ldg(bv + c * 8 + 5));
-            uv.w = pack_half2(__ldg(bv + c * 8 + 6), __ldg(bv + c * 8 + 7));
-            const int off = r * 128 + ((c ^ (r & 7)) << 4);
-            *reinterpret_cast<uint4*>(kvs + off) = uk;
-            *reinterpret_cast<uint4*>(kvs + KVH + off) = uv;
-          }
-        }
-        fence_proxy_async_smem();
-        mbar_arrive(kv_fixed);
       } else {
         const int tok = un.slab * 256 + qrow;
         qy = tok / WIN; qx = tok % WIN;
@@ -393,13 +432,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
 #pragma unroll
           for (int c = 0; c < HALF / 32; ++c) {
             uint32_t r32[32];
-            tmem_ld_32x32(tS + half * HALF + c * 32, r32);
+            tmem_ld_32x32((kSepT ? tT : tS) + half * HALF + c * 32, r32);
 #pragma unroll
             for (int i = 0; i < 32; ++i) scratch[(c * 32 + i) * 128 + row] = __uint_as_float(r32[i]);
           }
           if (half == 1) {
             tc_fence_before_sync();
-            mbar_arrive(&s_free[g]);                // T consumed: S(0) may overwrite it
+            mbar_arrive(kSepT ? &t_free[g] : &s_free[g]);   // T consumed: the region may be overwritten
           }
           const int sh = (half == 0 ? sy : sx) + WIN - 1;
 #pragma unroll
@@ -422,6 +461,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         const bool tr = p.trace && blockIdx.x == 0 && warp == 4 && lane == 0 && ui == 0;
         long long* trp = p.trace + jb * 8;
         if (tr) trp[0] = clock64();
+        if (jb == 0 && p.trace && blockIdx.x == 0 && warp == 4 && lane == 0 && ui < 8) p.trace[128 + ui] = clock64();
         mbar_wait(&s_ready[g], par);
         if (tr) trp[1] = clock64();
         tc_fence_after_sync();
@@ -463,7 +503,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
                   v = __fadd2_rn(v, make_float2(d, d));
                 }
                 y2[c * 16 + j] = v;
-                mq[j & 3] = fmaxf(mq[j & 3], fmaxf(v.x, v.y));
+                mq[j & 3] = fmax3(mq[j & 3], v.x, v.y);
               }
               m_blk = fmaxf(m_blk, fmaxf(fmaxf(mq[0], mq[1]), fmaxf(mq[2], mq[3])) + rh[0]);
             } else {
@@ -478,7 +518,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
                                  sl2, __fadd2_rn(make_float2(rh, rh), relw2[(key % WIN) / 2]));
                 }
                 y2[c * 16 + j] = v;
-                mq[j & 3] = fmaxf(mq[j & 3], fmaxf(v.x, v.y));
+                mq[j & 3] = fmax3(mq[j & 3], v.x, v.y);
               }
               m_blk = fmaxf(m_blk, fmaxf(fmaxf(mq[0], mq[1]), fmaxf(mq[2], mq[3])));
             }
@@ -519,15 +559,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             const float sub = rhc[c] - m_ref;
             const float2 sub2 = make_float2(sub, sub);
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) {
+            for (int j = 0; j < 16; j += 4) {
               const float2 a0 = __fadd2_rn(y2[c * 16 + j], sub2);
               const float2 a1 = __fadd2_rn(y2[c * 16 + j + 1], sub2);
+              const float2 a2 = __fadd2_rn(y2[c * 16 + j + 2], sub2);
+              const float2 a3 = __fadd2_rn(y2[c * 16 + j + 3], sub2);
               const float2 p0 = make_float2(ex2_approx(a0.x), ex2_approx(a0.y));
-              const float2 p1 = make_float2(ex2_approx(a1.x), ex2_poly3(a1.y));   // 1 in 4 on the FMA pipe
-              lsa = __fadd2_rn(lsa, p0);
-              lsb = __fadd2_rn(lsb, p1);
+              const float2 p1 = make_float2(ex2_approx(a1.x), ex2_approx(a1.y));
+              const float2 p2 = make_float2(ex2_approx(a2.x), ex2_approx(a2.y));
+              // kPoly: 1 in 4 on the (packed) FMA pipe instead of the MUFU
+              const float2 p3 = kPoly ? ex2_poly3_2(a3) : make_float2(ex2_approx(a3.x), ex2_approx(a3.y));
+              lsa = __fadd2_rn(lsa, __fadd2_rn(p0, p1));
+              lsb = __fadd2_rn(lsb, __fadd2_rn(p2, p3));
               pk[c * 16 + j] = pack_half2(p0.x, p0.y);
               pk[c * 16 + j + 1] = pack_half2(p1.x, p1.y);
+              pk[c * 16 + j + 2] = pack_half2(p2.x, p2.y);
+              pk[c * 16 + j + 3] = pack_half2(p3.x, p3.y);
             }
             if (g == 0 && jb == 0 && c == 1) mbar_arrive(stagger);   // ~half a block into the unit
           }
@@ -561,6 +608,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       }
 
       // ---- epilogue of the unit: O / l -> global ----
+      if (p.trace && blockIdx.x == 0 && warp == 4 && lane == 0 && ui < 8) p.trace[120 + ui] = clock64();
       mbar_wait(&pv_done[g], static_cast<uint32_t>((bcnt + NBLK - 1) & 1));
       tc_fence_after_sync();
       {
@@ -584,6 +632,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         }
         tc_fence_before_sync();
       }
+      if (p.trace && blockIdx.x == 0 && warp == 4 && lane == 0 && ui < 8) p.trace[136 + ui] = clock64();
       bcnt += NBLK;
     }
   }

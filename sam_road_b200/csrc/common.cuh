@@ -361,6 +361,25 @@ __device__ __forceinline__ float ex2_poly3(float x) {
   p = fmaf(p, f, 0.9999244809150696f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
+// three-input maximum (FMNMX3, sm_100)
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// Two at a time on the packed fp32x2 pipe (same coefficients and rounding per lane as ex2_poly3).
+__device__ __forceinline__ float2 ex2_poly3_2(float2 x) {
+  x = make_float2(fmaxf(x.x, -125.0f), fmaxf(x.y, -125.0f));
+  const float2 t = __fadd2_rn(x, make_float2(12582912.0f, 12582912.0f));
+  const float2 r = __fadd2_rn(t, make_float2(-12582912.0f, -12582912.0f));
+  const float2 f = __ffma2_rn(r, make_float2(-1.0f, -1.0f), x);
+  float2 p = __ffma2_rn(make_float2(0.05592203512787819f, 0.05592203512787819f), f,
+                        make_float2(0.24264007806777954f, 0.24264007806777954f));
+  p = __ffma2_rn(p, f, make_float2(0.6931210160255432f, 0.6931210160255432f));
+  p = __ffma2_rn(p, f, make_float2(0.9999244809150696f, 0.9999244809150696f));
+  return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23)),
+                     __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23)));
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }

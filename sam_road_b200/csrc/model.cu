@@ -1048,6 +1048,6 @@ extern "C" int samroad_op_attention(const void* qkv16, const float* qkv_bias, co
                            win, heads, head_dim, static_cast<__half*>(out16),
                            static_cast<cudaStream_t>(stream));
 }
-extern "C" void samroad_debug_force_simt_attention(int on) { attention_force_simt(on != 0); }
+extern "C" void samroad_debug_force_simt_attention(int on) { attention_force_simt(on); }
 extern "C" void samroad_debug_attention_trace(void* dev_buf) { attention_set_trace(static_cast<long long*>(dev_buf)); }
 extern "C" void samroad_debug_disable_2cta_gemm(int off) { gemm_disable_2cta(off); }
