@@ -118,4 +118,25 @@ int make_tmap_f16_4d(CUtensorMap* out, const void* base, const uint64_t dims[4],
   return 0;
 }
 
+// fp32 4-D map without swizzle (dense smem box), strides in bytes
+int make_tmap_f32_4d_dense(CUtensorMap* out, const void* base, const uint64_t dims[4],
+                           const uint64_t strides_bytes[3], const uint32_t box[4]) {
+  PFN_encodeTiled fn = get_encode_fn();
+  SRB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled driver entry point not available");
+  SRB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15u) == 0, "TMA base %p not 16-byte aligned",
+              base);
+  cuuint64_t gdim[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t gstr[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  for (int i = 0; i < 3; ++i)
+    SRB_REQUIRE(gstr[i] % 16 == 0, "TMA stride %d = %llu B not a multiple of 16", i,
+                (unsigned long long)gstr[i]);
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), gdim, gstr, bx,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SRB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(4D f32) failed (%d)", (int)r);
+  return 0;
+}
+
 }  // namespace srb

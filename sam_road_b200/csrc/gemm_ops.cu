@@ -1,4 +1,6 @@
 // sam_road_b200 :: GEMM instantiations and tile-shape dispatch.
+#include <cstring>
+
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
 #include "gemm_tc2r.cuh"
@@ -48,6 +50,10 @@ int gemm_f32out(const __half* A, int lda, const __half* W, int ldw, int M, int N
       if (g_resid_variant == 1) return launch_gemm_tc2_resid<4, 3, false>(A, lda, W, ldw, M, N, K, bias, out, ldo, st);
       return launch_gemm_tc2_resid<5, 2, true>(A, lda, W, ldw, M, N, K, bias, out, ldo, st);
     }
+    // out = A.W^T + b + pos[m % pos_rows] (patch embedding + pos_embed): addend streamed by TMA
+    if (!g_disable_tma_resid && resid == nullptr && pos != nullptr && bias != nullptr && pos_rows % 32 == 0 &&
+        (reinterpret_cast<uintptr_t>(out) & 15u) == 0 && (reinterpret_cast<uintptr_t>(pos) & 15u) == 0)
+      return launch_gemm_tc2_resid<4, 3, false>(A, lda, W, ldw, M, N, K, bias, out, ldo, st, pos, N, pos_rows);
     return launch_gemm_tc2<EpiF32>(A, lda, W, ldw, M, N, K, p, st);
   }
   if (use_bn256(M, N)) return launch_gemm_tc<256, 3, EpiF32>(A, lda, W, ldw, M, N, K, p, st);
@@ -70,7 +76,19 @@ int gemm_ln(const __half* A, int lda, const __half* W, int ldw, int M, int N, in
 int gemm_dec_final(const __half* A, int lda, const __half* W, int ldw, int M, int K,
                    const float* bias3, const float* w4, const float* bias4, int s, int P,
                    float* scores, float* logits, cudaStream_t st) {
-  EpiDecFinal::Params p{scores, logits, bias3, w4, bias4, s, P};
+  EpiDecFinal::Params p;
+  memset(&p, 0, sizeof(p));
+  SRB_REQUIRE(P == 16 * s && M % (16 * s * s) == 0, "gemm_dec_final: M=%d s=%d P=%d inconsistent", M, s, P);
+  const int B = M / (16 * s * s);
+  const uint64_t rowb = static_cast<uint64_t>(P) * 2 * sizeof(float);
+  const uint64_t dims[4] = {static_cast<uint64_t>(P) * 2, 2, 2, static_cast<uint64_t>(B) * P / 4};
+  const uint64_t strides[3] = {rowb, 2 * rowb, 4 * rowb};
+  const uint32_t box[4] = {64, 2, 1, 4};
+  if (scores) { if (int rc = make_tmap_f32_4d_dense(&p.tm_scores, scores, dims, strides, box)) return rc; }
+  if (logits) { if (int rc = make_tmap_f32_4d_dense(&p.tm_logits, logits, dims, strides, box)) return rc; }
+  p.has_scores = scores != nullptr;
+  p.has_logits = logits != nullptr;
+  p.bias3 = bias3; p.w4 = w4; p.bias4 = bias4; p.s = s; p.P = P;
   return launch_gemm_tc<128, 5, EpiDecFinal>(A, lda, W, ldw, M, 128, K, p, st);
 }
 

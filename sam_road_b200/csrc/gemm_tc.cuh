@@ -26,6 +26,8 @@
 //   ConvTranspose2d(k=2,s=2) as GEMM        model.py:286-295
 #pragma once
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "ops.h"
 
@@ -323,61 +325,87 @@ struct EpiLN {
 // d = di*2 + dj (see decoder weight packing in pack.cu).
 // ------------------------------------------------------------------------------------------------
 struct EpiDecFinal {
-  static constexpr bool kSplitCols = false;
+  static constexpr bool kSplitCols = true;     // warps 2-5: sub-pixels d3 = 0,1; warps 6-9: d3 = 2,3
   struct Params {
-    float* scores;        // [B, P, P, 2] or null
-    float* logits;        // [B, P, P, 2] or null
+    // [B, P, P, 2] fp32 seen as 4-D (x: 2P floats | di: 2 | h: 2 | k: B*P/4), image row = 4k + 2h + di;
+    // box {64 floats, 2, 1, 4}: the 2 x 16 output pixels x 8 rows one warp produces per tile and half
+    CUtensorMap tm_scores, tm_logits;
+    int has_scores, has_logits;
     const float* bias3;   // [32]
     const float* w4;      // [32 ci][8 = (di,dj,co)] fp32
     const float* bias4;   // [2]
     int s;                // feature map side (P/16)
     int P;
   };
+  // One lane = one stage-3 pixel (tile row), this warp's column half = two of its four 2x-upsampled
+  // sub-pixels d3; per sub-pixel: h = GELU(acc + b3) (32 channels, packed fp32x2 math), the final
+  // ConvT(32->2,k2,s2) as 8 dot products, sigmoid.  The warp's 32 rows are 2 adjacent tokens, i.e. a
+  // 16-row x 32-pixel patch of the mask of which this half owns rows 4k + 2*half + di: staged in smem
+  // as the dense TMA box and written with one 4-D TMA store per output (whole 128 B lines, where the
+  // old direct epilogue scattered 16 B pieces).
   static __device__ __forceinline__ void run(const Params& p, int m0, int M, int n_base, int n_cols,
-                                             const TmemRow& row, float* /*scratch*/, int lane) {
+                                             const TmemRow& row, float* scratch, int lane) {
+    const int half = n_base >> 6;
     const int m = m0 + lane;
-    const bool valid = m < M;
-    // decode pixel hierarchy of this row
     const int d2 = m & 3, d1 = (m >> 2) & 3;
-    const int pix = m >> 4;
-    const int ss = p.s * p.s;
-    const int b = pix / ss;
-    const int ij = pix - b * ss;
-    const int i = ij / p.s, j = ij - i * p.s;
-    const int y2 = ((i * 2 + (d1 >> 1)) * 2 + (d2 >> 1));      // row at 4s resolution
-    const int x2 = ((j * 2 + (d1 & 1)) * 2 + (d2 & 1));
-    const float b40 = __ldg(p.bias4 + 0), b41 = __ldg(p.bias4 + 1);
-    for (int c = 0; c < 4; ++c) {                              // c = d3 (n_base == 0, n_cols == 128)
+    const int tl = lane >> 4;                                   // which of the warp's two tokens
+    const int k = (d1 >> 1) * 2 + (d2 >> 1);                    // image row group inside the token
+    const int xq = (d1 & 1) * 2 + (d2 & 1);                     // 4-pixel column group inside the token
+    float* sS = scratch;                                        // [k 4][di 2][64 floats]
+    float* sL = scratch + 512;
+    const float2 b4 = make_float2(__ldg(p.bias4 + 0), __ldg(p.bias4 + 1));
+    if (lane == 0) bulk_wait_group_read<0>();                   // previous tile's stores have left smem
+    __syncwarp();
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
       float v[32];
-      row.load(c, v);
-      float o[8];
+      row.load(cc, v);
+      float2 o[4];                                              // (di,dj) x co
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] = (k & 1) ? b41 : b40;
+      for (int q = 0; q < 4; ++q) o[q] = b4;
 #pragma unroll
-      for (int ci = 0; ci < 32; ++ci) {
-        const float h = gelu_erf(v[ci] + __ldg(p.bias3 + ci));
-        const float4 wa = __ldg(reinterpret_cast<const float4*>(p.w4 + ci * 8));
-        const float4 wb = __ldg(reinterpret_cast<const float4*>(p.w4 + ci * 8 + 4));
-        o[0] = fmaf(h, wa.x, o[0]); o[1] = fmaf(h, wa.y, o[1]);
-        o[2] = fmaf(h, wa.z, o[2]); o[3] = fmaf(h, wa.w, o[3]);
-        o[4] = fmaf(h, wb.x, o[4]); o[5] = fmaf(h, wb.y, o[5]);
-        o[6] = fmaf(h, wb.z, o[6]); o[7] = fmaf(h, wb.w, o[7]);
+      for (int ci = 0; ci < 32; ci += 2) {
+        const float2 bb = __ldg(reinterpret_cast<const float2*>(p.bias3 + ci));
+        const float2 hh = gelu_erf_fast2(__fadd2_rn(make_float2(v[ci], v[ci + 1]), bb));
+        const float4* wp = reinterpret_cast<const float4*>(p.w4 + ci * 8);
+        const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3);
+        const float2 h0 = make_float2(hh.x, hh.x), h1 = make_float2(hh.y, hh.y);
+        o[0] = __ffma2_rn(h0, make_float2(w0.x, w0.y), o[0]);
+        o[1] = __ffma2_rn(h0, make_float2(w0.z, w0.w), o[1]);
+        o[2] = __ffma2_rn(h0, make_float2(w1.x, w1.y), o[2]);
+        o[3] = __ffma2_rn(h0, make_float2(w1.z, w1.w), o[3]);
+        o[0] = __ffma2_rn(h1, make_float2(w2.x, w2.y), o[0]);
+        o[1] = __ffma2_rn(h1, make_float2(w2.z, w2.w), o[1]);
+        o[2] = __ffma2_rn(h1, make_float2(w3.x, w3.y), o[2]);
+        o[3] = __ffma2_rn(h1, make_float2(w3.z, w3.w), o[3]);
       }
-      if (valid) {
-        const int y3 = y2 * 2 + (c >> 1), x3 = x2 * 2 + (c & 1);   // 8s resolution
 #pragma unroll
-        for (int di = 0; di < 2; ++di) {
-          const size_t off =
-              ((static_cast<size_t>(b) * p.P + (y3 * 2 + di)) * p.P + x3 * 2) * 2;
-          const float4 lg = make_float4(o[di * 4 + 0], o[di * 4 + 1], o[di * 4 + 2], o[di * 4 + 3]);
-          if (p.logits) *reinterpret_cast<float4*>(p.logits + off) = lg;
-          if (p.scores)
-            *reinterpret_cast<float4*>(p.scores + off) =
-                make_float4(sigmoidf_(lg.x), sigmoidf_(lg.y), sigmoidf_(lg.z), sigmoidf_(lg.w));
-        }
+      for (int di = 0; di < 2; ++di) {
+        const int off = (k * 2 + di) * 64 + (tl * 16 + (xq * 2 + cc) * 2) * 2;
+        const float4 lg = make_float4(o[di * 2].x, o[di * 2].y, o[di * 2 + 1].x, o[di * 2 + 1].y);
+        if (p.has_logits) *reinterpret_cast<float4*>(sL + off) = lg;
+        if (p.has_scores)
+          *reinterpret_cast<float4*>(sS + off) =
+              make_float4(sigmoidf_(lg.x), sigmoidf_(lg.y), sigmoidf_(lg.z), sigmoidf_(lg.w));
       }
     }
-    (void)n_base; (void)n_cols;
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0 && m0 < M) {
+      const int pix0 = m0 >> 4;                                 // first of the warp's two tokens
+      const int ss = p.s * p.s;
+      const int b = pix0 / ss;
+      const int ij = pix0 - b * ss;
+      const int i = ij / p.s, j = ij - i * p.s;
+      const int c0 = j * 32, c3 = (b * p.P + i * 16) >> 2;
+      if (p.has_scores) tma_store_4d(&p.tm_scores, sS, c0, 0, half, c3);
+      if (p.has_logits) tma_store_4d(&p.tm_logits, sL, c0, 0, half, c3);
+      bulk_commit_group();
+    }
+    (void)n_cols;
+  }
+  static __device__ __forceinline__ void drain(int lane) {
+    if (lane == 0) bulk_wait_group<0>();
   }
 };
 
@@ -397,7 +425,7 @@ struct GemmSmem {
 template <int BN, int STAGES, class Epi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               int M, int N, int K, typename Epi::Params ep) {
+               int M, int N, int K, const __grid_constant__ typename Epi::Params ep) {
   using SM = GemmSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -515,6 +543,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         as ^= 1;
         if (as == 0) aphase ^= 1u;
       }
+      if constexpr (std::is_same<Epi, EpiDecFinal>::value) EpiDecFinal::drain(lane);
     }
   }
 

@@ -35,7 +35,7 @@ struct Gemm2Smem {
 // encoder are short of (tools/gemm_probe.py: main loop alone 1.55 PFLOP/s).
 __device__ __forceinline__ void epi_f16_pack_chunk(const float (&v)[32], const float* __restrict__ bias_n,
                                                    int act, uint8_t* row_base, uint32_t piece0,
-                                                   uint32_t sw) {
+                                                   uint32_t sw, bool valid = true) {
   const float4* bp = reinterpret_cast<const float4*>(bias_n);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -59,7 +59,7 @@ __device__ __forceinline__ void epi_f16_pack_chunk(const float (&v)[32], const f
     u.y = pack_half2(x[1].x, x[1].y);
     u.z = pack_half2(x[2].x, x[2].y);
     u.w = pack_half2(x[3].x, x[3].y);
-    *reinterpret_cast<uint4*>(row_base + (((piece0 + static_cast<uint32_t>(i)) ^ sw) << 4)) = u;
+    if (valid) *reinterpret_cast<uint4*>(row_base + (((piece0 + static_cast<uint32_t>(i)) ^ sw) << 4)) = u;
   }
 }
 
@@ -183,26 +183,42 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     static_cast<uint32_t>(as * BN + col0)};
         if constexpr (kTmaOut) {
           if (ep.act != ACT_PROBE_SKIP) {
-#pragma unroll 1
-            for (int h = 0; h < 2; ++h, ++gs) {
-              uint8_t* buf = obuf + (gs & 1) * kGemm2OutBytes;
-              if (lane == 0) bulk_wait_group_read<1>();     // the store two blocks ago has left buf
-              __syncwarp();
-              const int n0 = n_blk * BN + col0 + h * 64;
+            // the TMEM load of chunk c+1 is in flight while chunk c is converted and stored
+            uint32_t rb[2][32];
+            tmem_ld_32x32_nowait(row.taddr, rb[0]);
 #pragma unroll
-              for (int cc = 0; cc < 2; ++cc) {
-                float v[32];
-                row.load(2 * h + cc, v);
-                epi_f16_pack_chunk(v, ep.bias ? ep.bias + n0 + cc * 32 : nullptr, ep.act,
-                                   buf + lane * 128, static_cast<uint32_t>(cc * 4), sw);
+            for (int c = 0; c < 4; ++c) {
+              const int h = c >> 1, cc = c & 1;
+              uint8_t* buf = obuf + ((gs + h) & 1) * kGemm2OutBytes;
+              const int n0 = n_blk * BN + col0 + h * 64;
+              if (cc == 0) {
+                if (lane == 0) bulk_wait_group_read<1>();   // the store two blocks ago has left buf
+                __syncwarp();
               }
-              fence_proxy_async_smem();
-              __syncwarp();
-              if (lane == 0) {
-                tma_store_2d(&tmO, buf, n0, m0);
-                bulk_commit_group();
+              tmem_ld_wait();
+              if (c + 1 < 4) tmem_ld_32x32_nowait(row.taddr + static_cast<uint32_t>(c + 1) * 32u, rb[(c + 1) & 1]);
+              float v[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rb[c & 1][i]);
+              if (ep.act & ACT_PROBE_DIRECT) {     // A/B: registers -> st.global, no smem, no TMA
+                const int m = m0 + lane;
+                epi_f16_pack_chunk(v, ep.bias ? ep.bias + n0 + cc * 32 : nullptr, ep.act & 0x3f,
+                                   reinterpret_cast<uint8_t*>(ep.out + static_cast<size_t>(m < M ? m : 0) * ep.ldo + n0),
+                                   static_cast<uint32_t>(cc * 4), 0u, m < M);
+                continue;
+              }
+              epi_f16_pack_chunk(v, ep.bias ? ep.bias + n0 + cc * 32 : nullptr, ep.act & 0x3f,
+                                 buf + lane * 128, static_cast<uint32_t>(cc * 4), sw);
+              if (cc == 1 && !(ep.act & ACT_PROBE_NOTMA)) {
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                  tma_store_2d(&tmO, buf, n0, m0);
+                  bulk_commit_group();
+                }
               }
             }
+            gs += 2;
           }
         } else {
           Epi::run(ep, m0, M, n_blk * BN + col0, n_cols, row, nullptr, lane);

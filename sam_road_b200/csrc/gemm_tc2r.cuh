@@ -30,8 +30,8 @@ struct Gemm2RSmem {
 template <int STAGES, int NB, bool kReduce>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_tc2_resid_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                      const __grid_constant__ CUtensorMap tmX, int M, int N, int K,
-                      const float* __restrict__ bias) {
+                      const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmR,
+                      int M, int N, int K, const float* __restrict__ bias, int load_rows) {
   using SM = Gemm2RSmem<STAGES, NB>;
   constexpr int BN = 256;
   extern __shared__ uint8_t smem_raw[];
@@ -61,6 +61,7 @@ gemm_tc2_resid_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmX);
+    if (!kReduce) tma_prefetch_desc(&tmR);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 2);
       mbar_init(&empty_bar[s], 1);
@@ -147,25 +148,33 @@ gemm_tc2_resid_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         int x, y;
         coords(g, x, y);
         mbar_arrive_expect_tx(&rfull[g], kGemm2RBlockBytes);
-        tma_load_2d(rbuf + g * kGemm2RBlockBytes, &tmX, &rfull[g], x, y);
+        tma_load_2d(rbuf + g * kGemm2RBlockBytes, &tmR, &rfull[g], x, load_rows > 0 ? y % load_rows : y);
       }
     }
     int as = 0;
     uint32_t aphase = 0;
     const uint32_t sw = static_cast<uint32_t>(lane & 7);
-    for (int g = 0; g < total; ++g) {
+    uint32_t rb[2][32];
+    for (int t4 = 0; t4 < total; t4 += 4) {
+#pragma unroll
+     for (int c = 0; c < 4; ++c) {
+      const int g = t4 + c;
       const int b = g % NB;
-      const int c = g & 3;
       int x, y;
       coords(g, x, y);
       if (c == 0) {
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after_sync();
       }
+      // accumulator block c+1 is already on its way from TMEM while block c is processed
+      const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                            static_cast<uint32_t>(as * BN + half * 128);
+      if (c == 0) tmem_ld_32x32_nowait(trow, rb[0]);
+      tmem_ld_wait();
       float v[32];
-      TmemRow row{tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                  static_cast<uint32_t>(as * BN + half * 128)};
-      row.load(c, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rb[c & 1][i]);
+      if (c < 3) tmem_ld_32x32_nowait(trow + static_cast<uint32_t>(c + 1) * 32u, rb[(c + 1) & 1]);
       float4* mine = reinterpret_cast<float4*>(rbuf + b * kGemm2RBlockBytes + lane * 128);
       const float4* bp = reinterpret_cast<const float4*>(bias + x);
       if (kReduce) {
@@ -208,7 +217,8 @@ gemm_tc2_resid_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             coords(gn, xn, yn);
             const int bn = gn % NB;
             mbar_arrive_expect_tx(&rfull[bn], kGemm2RBlockBytes);
-            tma_load_2d(rbuf + bn * kGemm2RBlockBytes, &tmX, &rfull[bn], xn, yn);
+            tma_load_2d(rbuf + bn * kGemm2RBlockBytes, &tmR, &rfull[bn], xn,
+                        load_rows > 0 ? yn % load_rows : yn);
           }
         }
       }
@@ -222,6 +232,7 @@ gemm_tc2_resid_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         as ^= 1;
         if (as == 0) aphase ^= 1u;
       }
+     }
     }
     if (lane == 0) bulk_wait_group<0>();
   }
@@ -232,9 +243,12 @@ gemm_tc2_resid_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 }
 
 // X[M, ldx] (fp32, in place) += A.W^T + bias.   N % 256 == 0, bias != null.
+// kReduce: X += A.W^T + bias (L2 reduce-add).  !kReduce: X = A.W^T + bias + R[m % load_rows] with R
+// streamed through smem (R = X for the in-place shortcut, R = pos_embed for the patch embedding).
 template <int STAGES, int NB, bool kReduce>
 int launch_gemm_tc2_resid(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K,
-                          const float* bias, float* X, int ldx, cudaStream_t stream) {
+                          const float* bias, float* X, int ldx, cudaStream_t stream,
+                          const float* R = nullptr, int ldr = 0, int load_rows = 0) {
   using SM = Gemm2RSmem<STAGES, NB>;
   SRB_REQUIRE(N % 256 == 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldx % 4 == 0,
               "gemm2r: bad shape N=%d K=%d", N, K);
@@ -242,6 +256,13 @@ int launch_gemm_tc2_resid(const __half* A, int lda, const __half* W, int ldw, in
   if (int rc = make_tmap_f16_2d(&tmA, A, M, K, lda, 128)) return rc;
   if (int rc = make_tmap_f16_2d(&tmB, W, N, K, ldw, 128)) return rc;
   if (int rc = make_tmap_f32_2d(&tmX, X, M, N, ldx, 32)) return rc;
+  CUtensorMap tmR = tmX;
+  if (R != nullptr && R != X) {
+    SRB_REQUIRE(!kReduce && load_rows > 0 && load_rows % 32 == 0, "gemm2r: bad addend rows %d", load_rows);
+    if (int rc = make_tmap_f32_2d(&tmR, R, load_rows, N, ldr, 32)) return rc;
+  } else {
+    load_rows = 0;
+  }
   auto kern = gemm_tc2_resid_kernel<STAGES, NB, kReduce>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -251,7 +272,7 @@ int launch_gemm_tc2_resid(const __half* A, int lda, const __half* W, int ldw, in
   const int num_tiles = ((M + 255) / 256) * (N / 256);
   const int max_clusters = device_sm_count() / 2;
   const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
-  kern<<<2 * clusters, kGemmThreads, SM::kTotal, stream>>>(tmA, tmB, tmX, M, N, K, bias);
+  kern<<<2 * clusters, kGemmThreads, SM::kTotal, stream>>>(tmA, tmB, tmX, tmR, M, N, K, bias, load_rows);
   SRB_CUDA_OK(cudaGetLastError());
   note_launch(1);
   return 0;

@@ -14,7 +14,9 @@ enum Act : int {
   // tools/gemm_probe.py only: epilogue ablations that do NOT produce the result
   ACT_PROBE_SKIP = 100,        // release the accumulator untouched (main-loop ceiling)
   ACT_PROBE_TMEM = 101,        // TMEM loads only
-  ACT_PROBE_NOSTORE = 102      // full GELU epilogue without the global stores
+  ACT_PROBE_NOSTORE = 102,     // full GELU epilogue without the global stores
+  ACT_PROBE_NOTMA = 0x80,      // flag (2-CTA fp16 epilogue): everything but the TMA store (no output)
+  ACT_PROBE_DIRECT = 0x40      // flag (2-CTA fp16 epilogue): registers -> st.global instead of smem + TMA store
 };
 
 void set_last_error(const char* fmt, ...);

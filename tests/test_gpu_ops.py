@@ -137,6 +137,33 @@ def test_gemm_f32_inplace_shortcut_tma(M, N, K):
     assert torch.equal(outs[1], outs[2]) and torch.equal(outs[1], outs[3])
 
 
+@pytest.mark.parametrize("M,T", [(65536, 1024), (20480, 256), (30000, 1024)])
+def test_gemm_f32_pos_embed_tma(M, T):
+    """out = A.W^T + b + pos[m % T] (patch embedding + pos_embed, image_encoder.py:107-109) with the
+    addend streamed by TMA (2-CTA kernel) against fp32 torch math and the register-path epilogue."""
+    lib = _lib.load()
+    N = K = 768
+    A = _rand16((M, K), 1.0, 41)
+    W = _rand16((N, K), 1.0 / math.sqrt(K), 42)
+    bias = torch.randn(N, device=DEV)
+    pos = torch.randn(T, N, device=DEV)
+    ref = bias + pos[torch.arange(M, device=DEV) % T]
+    for m0 in range(0, M, 16384):
+        ref[m0:m0 + 16384] += A[m0:m0 + 16384].float() @ W.float().t()
+    outs = []
+    for mode in (0, 2):
+        lib.samroad_debug_disable_2cta_gemm(mode)
+        out = torch.full((M, N), float("nan"), device=DEV)
+        _lib.check(lib.samroad_op_gemm_f32(A.data_ptr(), K, W.data_ptr(), K, M, N, K, bias.data_ptr(),
+                                           None, pos.data_ptr(), T, out.data_ptr(), N, _st()), "gemm_f32 pos")
+        torch.cuda.synchronize()
+        outs.append(out)
+    lib.samroad_debug_disable_2cta_gemm(0)
+    tol = 2e-4 * max(1.0, ref.abs().max().item())
+    assert (outs[0] - ref).abs().max().item() < tol
+    assert (outs[0] - outs[1]).abs().max().item() < 4e-6 * max(1.0, ref.abs().max().item())
+
+
 @pytest.mark.parametrize("M,N,K,group,act", [(1024, 256, 768, 256, 0), (1024, 512, 256, 128, 1),
                                              (333, 128, 128, 128, 0), (20000, 512, 256, 128, 1),
                                              (2048, 256, 2304, 256, 0)])

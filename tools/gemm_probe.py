@@ -63,8 +63,8 @@ def f32_case(name, N, K):
     lib.samroad_debug_disable_2cta_gemm(0)
 
 
-ACTS = (("none", 0), ("gelu packed", 1), ("gelu scalar", 4), ("skip epilogue", 100))
-SKIP = ACTS[:1] + ACTS[3:4]
+ACTS = (("none", 0), ("gelu packed", 1), ("none direct st", 0x40), ("none, no TMA st", 0x80), ("gelu, no TMA st", 0x81), ("skip epilogue", 100))
+SKIP = ACTS[:1] + ACTS[4:5]
 which = set(sys.argv[1:])
 
 
@@ -77,7 +77,7 @@ if want("lin1"):
 if want("qkv"):
     f16_case("qkv", 2304, 768, SKIP)
 if want("k3072"):
-    f16_case("k3072", 3072, 3072, ACTS[:2] + ACTS[3:4])
+    f16_case("k3072", 3072, 3072, ACTS[:2] + ACTS[4:5])
 if want("shapes"):      # main-loop ceilings of the fp32-epilogue shapes
     f16_case("lin2shape", 768, 3072, SKIP)
     f16_case("projshape", 768, 768, SKIP)
