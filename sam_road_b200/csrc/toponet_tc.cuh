@@ -11,8 +11,12 @@
 //   smem  A buffer 32 KB  current fp16 GEMM A operand (x -> attention output -> x' -> hidden -> x'')
 //         KV buffer 66 KB k and v of the tile as fp16 rows (the x fp32 tile lands here by TMA first)
 //         weight ring 3 x 32 KB  the 18 [128x128] weight chunks streamed by TMA in consumption order
-// Warps: 0 = TMA producer, 1 = MMA issuer + TMEM allocator, 2..5 = the 128 token threads (epilogues,
-// attention on CUDA cores, LayerNorm, output_proj).  Key-padding semantics: masked
+// Warps: 0 = TMA producer, 1 = MMA issuer + TMEM allocator, 2..9 = 256 token threads, TWO per token
+// (warps w and w+4 share a TMEM lane quarter): epilogues, attention on CUDA cores, LayerNorm,
+// output_proj.  Part 0 owns columns 0..63 / heads 0,1 / the k rows, part 1 columns 64..127 / heads 2,3 /
+// the v rows; LayerNorm statistics and the output dot product are combined through a small smem
+// exchange.  The token work, not the GEMMs, bounds this kernel (two warps per scheduler hide twice the
+// latency of one).  Key-padding semantics: masked
 // keys are excluded from the softmax; masked slots report output_proj.bias.
 #pragma once
 
@@ -21,14 +25,15 @@
 
 namespace srb {
 
-constexpr int kTtcThreads = 192;
+constexpr int kTtcThreads = 320;
 constexpr int kTtcWStages = 3;
 constexpr int kTtcOffA = 0;                       // 2 k-blocks x 16 KB
 constexpr int kTtcOffKV = 32768;                  // 128 rows x 528 B (k|v fp16, padded) / x fp32 tile
 constexpr int kTtcKVStride = 528;
 constexpr int kTtcOffW = kTtcOffKV + 68608;       // 3 x 32 KB
 constexpr int kTtcOffBar = kTtcOffW + kTtcWStages * 32768;
-constexpr int kTtcSmemBytes = kTtcOffBar + 256 + 1024;
+constexpr int kTtcOffXch = kTtcOffBar + 256;      // 3 slots x 256 floats: partial sums of the two parts
+constexpr int kTtcSmemBytes = kTtcOffXch + 3 * 1024 + 1024;
 constexpr int kTtcChunksPerLayer = 6;             // Wq, Wk, Wv, Wo, W1, W2
 
 struct TtcLayerParams {
@@ -50,8 +55,8 @@ struct TtcParams {
   int num_tiles;
 };
 
-__device__ __forceinline__ void named_bar_sync_128() {
-  asm volatile("bar.sync 1, 128;" ::: "memory");
+__device__ __forceinline__ void named_bar_sync_tokens() {
+  asm volatile("bar.sync 1, 256;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(kTtcThreads, 1)
@@ -66,7 +71,7 @@ toponet_tc_kernel(const __grid_constant__ CUtensorMap tmX16, const __grid_consta
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTtcOffBar);
   uint64_t* x_full = bars + 0;      // TMA: x16 -> A buffer, x32 -> KV buffer
   uint64_t* a_free = bars + 1;      // MMA commit: last GEMM of the tile retired (A / KV reusable)
-  uint64_t* a_ready = bars + 2;     // 128 token threads: new A operand written
+  uint64_t* a_ready = bars + 2;     // 256 token threads: new A operand written
   uint64_t* acc_ready = bars + 3;   // MMA commit: GEMM result in TMEM
   uint64_t* w_full = bars + 4;      // [3]
   uint64_t* w_empty = bars + 7;     // [3]
@@ -81,7 +86,7 @@ toponet_tc_kernel(const __grid_constant__ CUtensorMap tmX16, const __grid_consta
     tma_prefetch_desc(&tmW);
     mbar_init(x_full, 1);
     mbar_init(a_free, 1);
-    mbar_init(a_ready, 128);
+    mbar_init(a_ready, 256);
     mbar_init(acc_ready, 1);
     for (int i = 0; i < kTtcWStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     fence_barrier_init();
@@ -153,12 +158,14 @@ toponet_tc_kernel(const __grid_constant__ CUtensorMap tmX16, const __grid_consta
   } else {
     // =========================== token threads ===========================
     const int quarter = warp & 3;
+    const int part = (warp - 2) >> 2;                 // 0: columns 0..63, 1: columns 64..127
     const int row = quarter * 32 + lane;
     const uint32_t tlane = static_cast<uint32_t>(quarter * 32) << 16;
     const uint32_t tAcc = tmem_base + tlane;          // cols [0,384)
     const uint32_t tRes = tmem_base + tlane + 384;    // cols [384,512)
     const int sw = row & 7;
     uint8_t* myA = sA + row * 128;
+    float* xch = reinterpret_cast<float*>(smem + kTtcOffXch);   // [3][2 parts][128 rows]
     int ti = 0, rc = 0;                               // tiles, acc_ready completions consumed
 
     auto write_a_chunk = [&](int c, const float (&v)[32]) {   // 32 fp32 -> fp16 into the swizzled A buffer
@@ -186,12 +193,20 @@ toponet_tc_kernel(const __grid_constant__ CUtensorMap tmX16, const __grid_consta
       for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(v[i]);
       tmem_st_32x32(taddr, r);
     };
+    // this thread's partial + the other part's partial of the same row (slot: 0 sum, 1 var, 2 dot)
+    auto combine = [&](int slot, float mine) -> float {
+      xch[slot * 256 + part * 128 + row] = mine;
+      named_bar_sync_tokens();
+      return mine + xch[slot * 256 + (part ^ 1) * 128 + row];
+    };
     // x = LayerNorm(res + acc + bias) ; res <- x ; optionally A buffer <- fp16(x); returns x.w_out
+    // (this part's two 32-column chunks; exact two-pass statistics over the whole row)
     auto residual_layernorm = [&](const float* bias, const float* gamma, const float* beta,
                                   bool write_a, const float* wdot) -> float {
       float sum = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = part * 2 + cc;
         float a[32], r[32];
         ld_chunk(tAcc + c * 32, a);
         ld_chunk(tRes + c * 32, r);
@@ -203,10 +218,11 @@ toponet_tc_kernel(const __grid_constant__ CUtensorMap tmX16, const __grid_consta
         st_chunk(tRes + c * 32, r);
       }
       tmem_st_wait();
-      const float mean = sum * (1.0f / 128.0f);
+      const float mean = combine(0, sum) * (1.0f / 128.0f);
       float var = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = part * 2 + cc;
         float r[32];
         ld_chunk(tRes + c * 32, r);
 #pragma unroll
@@ -215,10 +231,11 @@ toponet_tc_kernel(const __grid_constant__ CUtensorMap tmX16, const __grid_consta
           var = fmaf(d, d, var);
         }
       }
-      const float rstd = rsqrtf(var * (1.0f / 128.0f) + 1e-5f);
+      const float rstd = rsqrtf(combine(1, var) * (1.0f / 128.0f) + 1e-5f);
       float dot = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = part * 2 + cc;
         float r[32];
         ld_chunk(tRes + c * 32, r);
 #pragma unroll
@@ -252,7 +269,8 @@ toponet_tc_kernel(const __grid_constant__ CUtensorMap tmX16, const __grid_consta
       // ---- x (fp32) : smem (TMA, 4 boxes of [128 x 32 floats], 128B swizzle) -> TMEM residual ----
       mbar_wait(x_full, ti & 1);
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = part * 2 + cc;
         float v[32];
         const uint8_t* src = sKV + c * 16384 + row * 128;
 #pragma unroll
@@ -263,7 +281,9 @@ toponet_tc_kernel(const __grid_constant__ CUtensorMap tmX16, const __grid_consta
         st_chunk(tRes + c * 32, v);
       }
       tmem_st_wait();
-      named_bar_sync_128();                          // every thread is done with the x32 smem tile
+      tc_fence_before_sync();
+      named_bar_sync_tokens();                       // every thread is done with the x32 smem tile
+      tc_fence_after_sync();
 
       float dot = 0.f;
 #pragma unroll 1
@@ -273,7 +293,8 @@ toponet_tc_kernel(const __grid_constant__ CUtensorMap tmX16, const __grid_consta
         mbar_wait(acc_ready, rc & 1); ++rc;
         tc_fence_after_sync();
 #pragma unroll 1
-        for (int c = 0; c < 8; ++c) {                 // k: cols 128..255, v: cols 256..383
+        for (int cc = 0; cc < 4; ++cc) {              // part 0: k (cols 128..255), part 1: v (cols 256..383)
+          const int c = part * 4 + cc;
           float v[32];
           ld_chunk(tAcc + 128 + c * 32, v);
           uint8_t* dst = sKV + row * kTtcKVStride + ((c * 64) ^ (((row >> 4) & 1) << 6));
@@ -288,60 +309,61 @@ toponet_tc_kernel(const __grid_constant__ CUtensorMap tmX16, const __grid_consta
             *reinterpret_cast<uint4*>(dst + q4 * 16) = u;
           }
         }
-        named_bar_sync_128();
+        named_bar_sync_tokens();
         const uint8_t* kv0 = sKV + (row & ~15) * kTtcKVStride;   // first token of this sample
         const int sx = ((row >> 4) & 1) << 6;                    // odd samples: columns XOR 64 B
 #pragma unroll 1
-        for (int h = 0; h < 4; ++h) {
-          float q[32];
-          ld_chunk(tAcc + h * 32, q);
+        for (int hh2 = 0; hh2 < 2; ++hh2) {
+          const int h = part * 2 + hh2;
+          float2 q2[16];
+          {
+            float q[32];
+            ld_chunk(tAcc + h * 32, q);
 #pragma unroll
-          for (int i = 0; i < 32; ++i)   // torch MHA scales q by 1/sqrt(head_dim)
-            q[i] = (q[i] + __ldg(L.in_b + h * 32 + i)) * 0.17677669529663687f;
+            for (int i = 0; i < 16; ++i) {   // torch MHA scales q by 1/sqrt(head_dim)
+              const float2 bb = __ldg(reinterpret_cast<const float2*>(L.in_b + h * 32) + i);
+              q2[i] = make_float2((q[2 * i] + bb.x) * 0.17677669529663687f,
+                                  (q[2 * i + 1] + bb.y) * 0.17677669529663687f);
+            }
+          }
           float sc[16];
           float mx = -INFINITY;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const uint8_t* kp = kv0 + j * kTtcKVStride + ((h * 64) ^ sx);
-            float acc = 0.f;
+            float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
               const uint4 u = *reinterpret_cast<const uint4*>(kp + c4 * 16);
               const __half2* hh = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = __half22float2(hh[e]);
-                acc = fmaf(q[c4 * 8 + 2 * e], f.x, acc);
-                acc = fmaf(q[c4 * 8 + 2 * e + 1], f.y, acc);
-              }
+              for (int e = 0; e < 4; ++e) acc = __ffma2_rn(q2[c4 * 4 + e], __half22float2(hh[e]), acc);
             }
-            sc[j] = ((kmask >> j) & 1u) ? acc : -INFINITY;
+            sc[j] = ((kmask >> j) & 1u) ? acc.x + acc.y : -INFINITY;
             mx = fmaxf(mx, sc[j]);
           }
-          float o[32];
+          float2 o2[16];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = 0.f;
+          for (int i = 0; i < 16; ++i) o2[i] = make_float2(0.f, 0.f);
           float lsum = 0.f;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float pj = __expf(sc[j] - mx);       // exp(-inf) = 0 for masked keys
             lsum += pj;
+            const float2 pj2 = make_float2(pj, pj);
             const uint8_t* vp = kv0 + j * kTtcKVStride + ((256 + h * 64) ^ sx);
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
               const uint4 u = *reinterpret_cast<const uint4*>(vp + c4 * 16);
               const __half2* hh = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = __half22float2(hh[e]);
-                o[c4 * 8 + 2 * e] = fmaf(pj, f.x, o[c4 * 8 + 2 * e]);
-                o[c4 * 8 + 2 * e + 1] = fmaf(pj, f.y, o[c4 * 8 + 2 * e + 1]);
-              }
+              for (int e = 0; e < 4; ++e) o2[c4 * 4 + e] = __ffma2_rn(pj2, __half22float2(hh[e]), o2[c4 * 4 + e]);
             }
           }
           const float inv = 1.0f / lsum;
+          float o[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] *= inv;
+          for (int i = 0; i < 16; ++i) { o[2 * i] = o2[i].x * inv; o[2 * i + 1] = o2[i].y * inv; }
           write_a_chunk(h, o);                       // attention output columns h*32..h*32+31
         }
         tc_fence_before_sync();
@@ -358,7 +380,8 @@ toponet_tc_kernel(const __grid_constant__ CUtensorMap tmX16, const __grid_consta
         mbar_wait(acc_ready, rc & 1); ++rc;
         tc_fence_after_sync();
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = part * 2 + cc;
           float v[32];
           ld_chunk(tAcc + c * 32, v);
 #pragma unroll
@@ -377,7 +400,8 @@ toponet_tc_kernel(const __grid_constant__ CUtensorMap tmX16, const __grid_consta
         mbar_arrive(a_ready);     // l == 2: releases the accumulator columns for the next tile
       }
       // ================= output_proj + sigmoid =================
-      if (tok_ok) {
+      dot = combine(2, dot);
+      if (tok_ok && part == 0) {
         const float b = __ldg(p.out_b);
         const float lg = my_valid ? dot + b : b;
         if (p.logits) p.logits[tok] = lg;
