@@ -146,7 +146,8 @@ int samroad_op_attention(const void* qkv16, const float* qkv_bias, const float* 
 
 /* Test hook (bit mask): bit 0 routes samroad_op_attention / the encoder through the fp32 SIMT
  * attention kernel (the independent on-device checker of the tcgen05 kernel); bit 1 selects the
- * tcgen05 variant that evaluates 1 in 4 softmax exponentials as a polynomial on the FMA pipe (A/B
+ * tcgen05 variant that evaluates 1 in 4 softmax exponentials as a polynomial on the FMA pipe; bit 2
+ * starts softmax group 1 half a block late; bit 3 disables the groups' turn-taking on the MUFU (A/B
  * timing, tools/att_trace.py).  Not for production use. */
 void samroad_debug_force_simt_attention(int on);
 /* Test hook (bit mask): bit 0 routes every GEMM through the 1-CTA kernels (the 2-CTA cta_group::2

@@ -224,11 +224,12 @@ int pack_rel_table(const float* rel_h, const float* rel_w, int win, int hd, __ha
 }
 
 static bool g_force_simt = false;
-static bool g_no_stagger = false;
+static bool g_no_stagger = true;    // A/B hook (bit 2 set): start group 1 half a block late
+static bool g_alternate = true;     // A/B hook (bit 3 set): no turn-taking on the MUFU
 static bool g_poly = false;         // A/B hook: 1 in 4 softmax exponentials as a polynomial on the FMA pipe
 static long long* g_att_trace = nullptr;
 void attention_set_trace(long long* p) { g_att_trace = p; }
-void attention_force_simt(int mode) { g_force_simt = (mode & 1) != 0; g_poly = (mode & 2) != 0; g_no_stagger = (mode & 4) != 0; }
+void attention_force_simt(int mode) { g_force_simt = (mode & 1) != 0; g_poly = (mode & 2) != 0; g_no_stagger = (mode & 4) == 0; g_alternate = (mode & 8) == 0; }
 
 template <bool kWindow, int WIN>
 static int launch_attention_tc(const __half* qkv, const float* qkv_bias, const __half* tab, int B,
@@ -266,6 +267,7 @@ static int launch_attention_tc(const __half* qkv, const float* qkv_bias, const _
   p.num_units = units;
   p.trace = g_att_trace;
   p.no_stagger = g_no_stagger ? 1 : 0;
+  p.alternate = g_alternate ? 1 : 0;
   const int grid = units < device_sm_count() ? units : device_sm_count();   // persistent CTAs
   kern<<<grid, kAtcThreads, AtcSmem<kWindow>::kBytes, st>>>(tmQKV, tmTab, p);
   SRB_CUDA_OK(cudaGetLastError());

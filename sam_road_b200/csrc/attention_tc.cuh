@@ -63,6 +63,7 @@ struct AtcParams {
   int num_units;
   float scale_log2e;       // head_dim^-0.5 * log2(e)
   int no_stagger;          // A/B hook: do not delay group 1 by half a block
+  int alternate;           // A/B hook: strict alternation of the groups' exponential phases
   long long* trace;        // debug: 256 clock64 stamps of CTA 0 (softmax warp 4: 8 per block; MMA threads; unit phases), or null
 };
 
@@ -137,6 +138,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
   uint64_t* kv_seen = bars + 25;                // both issuers are past kv_fixed(ui) (paces warp 3)
   uint64_t* t_free = bars + 26;                 // [2] rel-pos projection T_g gathered (kSepT)
+  uint64_t* e_done = bars + 28;                 // [2] group g finished the exponentials of a block
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -150,7 +152,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     mbar_init(kv_fixed, 1);
     mbar_init(kv_seen, 2);
     mbar_init(stagger, 128);
-    for (int i = 0; i < 2; ++i) mbar_init(&t_free[i], 128);
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_free[i], 128); mbar_init(&e_done[i], 128); }
     for (int i = 0; i < kAtcKVStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 2); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_ready[i], 1);
@@ -307,9 +309,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
           mbar_arrive(kv_seen);
           tc_fence_after_sync();
         }
-        // the two groups share each SMSP's MUFU: start group 1 half a block behind group 0 so that
-        // one group's exponentials overlap the other's TMEM loads / max / P stores (8-block global
-        // units only; with the 2-block window units the delay costs more than it gains)
+        // A/B hook (off by default, superseded by the turn-taking below): start group 1 half a block
+        // behind group 0 so that one group's exponentials overlap the other's TMEM loads / max / P
+        // stores (8-block global units only)
         if (g == 1 && !kWindow && !p.no_stagger) mbar_wait(stagger, ui & 1);
         issue_s(0);
         for (int jb = 0; jb < NBLK; ++jb) {
@@ -550,6 +552,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             tmem_st_wait();
           }
         }
+        // ---- the two groups take turns on the MUFU: g0 b0, g1 b0, g0 b1, ... (global mode) ----
+        if constexpr (!kWindow) {
+          if (p.alternate) {
+            const int n = bcnt + jb;                 // this group's block ordinal over the whole launch
+            if (g == 0) { if (n > 0) mbar_wait(&e_done[1], static_cast<uint32_t>((n - 1) & 1)); }
+            else mbar_wait(&e_done[0], static_cast<uint32_t>(n & 1));
+          }
+        }
         // ---- p = 2^(y - m_ref) packed to fp16 in registers, row sum (packed partial sums) ----
         uint32_t pk[64];
         float2 lsa = make_float2(0.f, 0.f), lsb = make_float2(0.f, 0.f);
@@ -579,6 +589,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             if (g == 0 && jb == 0 && c == 1) mbar_arrive(stagger);   // ~half a block into the unit
           }
         }
+        if constexpr (!kWindow) { if (p.alternate) mbar_arrive(&e_done[g]); }
         l_run += (lsa.x + lsa.y) + (lsb.x + lsb.y);
         if (tr) trp[4] = clock64() + static_cast<long long>(l_run > 1e30f);
         // ---- P -> smem (swizzled) once PV(jb-1) has finished reading the buffer ----

@@ -67,7 +67,7 @@ inline int rel_table_rows(int win) { return 4 * win - 2 <= 64 ? 64 : 128; }
 int pack_rel_table(const float* rel_h, const float* rel_w, int win, int hd, __half* tab,
                    cudaStream_t st);
 // force the SIMT v1 attention kernel (tests use it as the independent on-device checker)
-void attention_force_simt(int mode);   // bit 0: SIMT kernel, bit 1: tcgen05 kernel with 1-in-4 polynomial exps
+void attention_force_simt(int mode);   // bit 0: SIMT kernel, bit 1: tcgen05 kernel with 1-in-4 polynomial exps, bit 2: half-block stagger, bit 3: no MUFU turn-taking
 void attention_set_trace(long long* device_buffer_128);   // debug: per-phase clock64 stamps of CTA 0
 
 // ---- TopoNet pieces (toponet.cu) -----------------------------------------------------------------------------

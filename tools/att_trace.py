@@ -27,7 +27,7 @@ for win in (32, 14):
     call = lambda: _lib.check(lib.samroad_op_attention(qkv.data_ptr(), bias.data_ptr(), rel_h.data_ptr(), rel_w.data_ptr(),
                                                        B, s, win, heads, hd, out.data_ptr(), torch.cuda.current_stream().cuda_stream), "att")
     for rep in range(2):
-        for label, mode in (("default", 0), ("no stagger", 4)):
+        for label, mode in (("default (turn-taking)", 0), ("free-running + stagger", 12), ("free-running", 8)):
             lib.samroad_debug_force_simt_attention(mode)
             print(f"win={win} {label}: {_time(call):.1f} us")
     lib.samroad_debug_force_simt_attention(0)
@@ -38,6 +38,7 @@ for win in (32, 14):
                                             B, s, win, heads, hd, out.data_ptr(), torch.cuda.current_stream().cuda_stream), "att")
     torch.cuda.synchronize()
     lib.samroad_debug_attention_trace(None)
+    lib.samroad_debug_force_simt_attention(0)
     t = tr.cpu().tolist()
     nblk = 8 if win == 32 else 2
     t0 = t[0]
