@@ -53,25 +53,59 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML every 10 ms when the binding
+    is importable (nvidia-ml-py), else one nvidia-smi query per 150 ms."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
         self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+        self.source = "nvidia-smi"
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._nvml = pynvml
+            self.source = "nvml"
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n = self._nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM))
+        try:
+            watts = n.nvmlDeviceGetPowerUsage(self._h) / 1000.0
+        except Exception:
+            watts = float("nan")
+        try:
+            mask = n.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        except Exception:
+            mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        bits = [getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)]
+        self.rows.append([str(sm), str(self._max), str(watts)] +
+                         ["Active" if mask & b else "Not Active" for b in bits])
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True,
-                                     text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits"], capture_output=True,
+                                         text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.15)
+            self._stop.wait(0.01 if self._nvml is not None else 0.15)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -83,17 +117,22 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        def num(x):
+            try:
+                return float(x)
+            except Exception:
+                return None
+        sm = sorted(v for v in (num(r[0]) for r in self.rows if r) if v is not None)
         reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
-            for n, v in zip(names, r[3:7]):
+            for n, v in zip(self.NAMES, r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        mx = max((float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()),
-                 default=None)
+        mx = max((v for v in (num(r[1]) for r in self.rows if len(r) > 1) if v is not None), default=None)
+        pw = [v for v in (num(r[2]) for r in self.rows if len(r) > 2) if v is not None and v == v]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "sm_mhz_min": sm[0] if sm else None, "power_w_max": max(pw) if pw else None,
+                "reasons": sorted(reasons), "samples": len(self.rows), "source": self.source}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -283,6 +322,12 @@ def run_native(args):
         return
 
     # ---- roofline of the dominant kernel class ---------------------------------------------------
+    # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernel classes captured
+    # with `ncu --set full` at this workload: profiles/r01_gemm_f16_v3_raw.csv, r01_gemm_resid_v3_raw.csv,
+    # r01_att_v5_raw.csv (tools/gpu/profile_r01.sh).  Only valid for the default batch of 64 tiles.
+    ncu_traffic = {"gemm_mlp_lin1": 105.511168e6 + 345.874176e6, "gemm_qkv": 104.280576e6 + 247.809280e6,
+                   "gemm_mlp_lin2": 613.990144e6 + 170.727168e6, "gemm_proj": 303.192576e6 + 143.959552e6,
+                   "attention_global": 302.227456e6 + 81.448448e6, "attention_window": 302.059520e6 + 78.373376e6}
     peaks = load_peaks()
     gemm_like = {k: v for k, v in kernels.items() if v["flops"] > 0}
     dom = max(gemm_like, key=lambda k: gemm_like[k]["ms"]) if gemm_like else None
@@ -292,7 +337,9 @@ def run_native(args):
         per_launch_ms = d["ms"] / d["launches"]
         achieved = d["flops"] / d["launches"] / (per_launch_ms * 1e-3) / 1e12
         roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"],
-                    "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": None,
+                    "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
+                    "traffic": ncu_traffic.get(dom) if args.batch == 64 else None,
+                    "traffic_source": "ncu --set full, profiles/r01_*_v3_raw.csv (bytes per launch)",
                     "peak_source": peaks["source"], "launches": d["launches"],
                     "avg_launch_ms": per_launch_ms,
                     "algorithmic_flops_per_launch": d["flops"] / d["launches"]}
@@ -371,7 +418,7 @@ def main():
     global _OUT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=CONFIG["INFER_BATCH_SIZE"])
