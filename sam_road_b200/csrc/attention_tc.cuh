@@ -419,6 +419,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         out_tok = static_cast<size_t>(un.b) * T + tok;
       }
       if (!active) continue;
+      if constexpr (kWindow) {
+        // A warp whose 32 query rows are all window padding (rows >= 196, or below the image edge)
+        // produces no output: it keeps the barrier protocol moving and computes nothing.  Its P rows
+        // keep whatever they held -- O rows are independent and these are never stored.
+        const int r0 = g * 128 + quarter * 32;
+        if (r0 >= KEYS || r0 / WIN >= ry) {
+          mbar_arrive(&t_free[g]);
+          for (int jb = 0; jb < NBLK; ++jb) {
+            const uint32_t par = static_cast<uint32_t>((bcnt + jb) & 1);
+            mbar_wait(&s_ready[g], par);
+            mbar_arrive(&s_free[g]);
+            if (jb > 0) mbar_wait(&pv_done[g], par ^ 1u);   // p_ready phase jb-1 is complete
+            mbar_arrive(&p_ready[g]);
+          }
+          bcnt += NBLK;
+          continue;
+        }
+      }
 
       // ---- rel-pos rows of this query, pre-multiplied by log2(e) ----
       // table rows: rel_pos_h at [0, 2K-1), rel_pos_w at [HALF, HALF + 2K-1)  (pack_rel_table)
