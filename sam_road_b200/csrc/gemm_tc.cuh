@@ -206,11 +206,14 @@ struct EpiF32 {
 // Epilogue 3: grouped row LayerNorm.  x = acc + bias + resid; per group of `group` consecutive
 // columns: y = (x - mean) / sqrt(var + eps) * gamma[n % group] + beta[n % group]; y = act(y).
 // The tile must hold whole groups (BN % group == 0).  Three TMEM passes (mean, var, write) keep the
-// exact two-pass variance of torch.  Outputs (each optional): fp16 row-major, fp32 row-major,
-// fp32 NCHW ([b, n, tok] with tok = m % tokens, b = m / tokens) for the API-visible embeddings.
+// exact two-pass variance of torch.  All eight epilogue warps work: the two warps of a TMEM lane
+// quarter split the tile's columns; when a group fits into one half they are independent, when it
+// spans the tile (neck: group = BN = 256) they combine their partial sums through their smem scratch
+// and a 64-thread named barrier.  Outputs (each optional): fp16 row-major, fp32 row-major, fp32 NCHW
+// ([b, n, tok] with tok = m % tokens, b = m / tokens) for the API-visible embeddings.
 // ------------------------------------------------------------------------------------------------
 struct EpiLN {
-  static constexpr bool kSplitCols = false;
+  static constexpr bool kSplitCols = true;
   struct Params {
     __half* out16;        // [M, ldo] or null
     float* out32;         // [M, ldo] or null
@@ -248,12 +251,19 @@ struct EpiLN {
     }
   }
   static __device__ __forceinline__ void run(const Params& p, int m0, int M, int n_base, int n_cols,
-                                             const TmemRow& row, float* /*scratch*/, int lane) {
+                                             const TmemRow& row, float* scratch, int lane) {
     const int m = m0 + lane;
     const bool valid = m < M;
-    const int cpg = p.group >> 5;              // chunks per group
-    const int ngroups = n_cols / p.group;
+    if (n_cols <= 0) return;
+    const bool shared = p.group > n_cols;              // one group spans both column halves
+    const int span = shared ? n_cols : p.group;        // columns of a group this warp owns
+    const int cpg = span >> 5;                         // chunks per group (mine)
+    const int ngroups = n_cols / span;
     const float inv_g = 1.0f / static_cast<float>(p.group);
+    // partner warp of the same lane quarter (warps 2+q and 6+q): scratch 4 warps away
+    const int half = (n_base / n_cols) & 1;
+    const float* partner = scratch + (half ? -4 : 4) * kGemmScratchFloats;
+    const int pair_bar = 1 + ((m0 >> 5) & 3);
     for (int g = 0; g < ngroups; ++g) {
       float mean = 0.f;
       for (int c = 0; c < cpg; ++c) {
@@ -261,6 +271,11 @@ struct EpiLN {
         load_x(p, m, valid, n_base + (g * cpg + c) * 32, g * cpg + c, row, v);
 #pragma unroll
         for (int i = 0; i < 32; ++i) mean += v[i];
+      }
+      if (shared) {
+        scratch[lane] = mean;
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        mean += partner[lane];
       }
       mean *= inv_g;
       float var = 0.f;
@@ -273,16 +288,25 @@ struct EpiLN {
           var = fmaf(d, d, var);
         }
       }
+      if (shared) {
+        scratch[32 + lane] = var;
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        var += partner[32 + lane];
+      }
       const float rstd = rsqrtf(var * inv_g + p.eps);
       for (int c = 0; c < cpg; ++c) {
         float v[32];
         const int n0 = n_base + (g * cpg + c) * 32;
         load_x(p, m, valid, n0, g * cpg + c, row, v);
-        const int gi = c * 32;
+        const int gi = n0 % p.group;                   // column inside its LayerNorm group
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float y = (v[i] - mean) * rstd * __ldg(p.gamma + gi + i) + __ldg(p.beta + gi + i);
-          v[i] = apply_act(y, p.act);
+        for (int i = 0; i < 32; i += 2) {
+          const float2 gm = __ldg(reinterpret_cast<const float2*>(p.gamma + gi + i));
+          const float2 bt = __ldg(reinterpret_cast<const float2*>(p.beta + gi + i));
+          float2 y = make_float2((v[i] - mean) * rstd * gm.x + bt.x, (v[i + 1] - mean) * rstd * gm.y + bt.y);
+          if (p.act == ACT_GELU) y = gelu_erf_fast2(y);
+          else if (p.act != ACT_NONE) y = make_float2(apply_act(y.x, p.act), apply_act(y.y, p.act));
+          v[i] = y.x; v[i + 1] = y.y;
         }
         if (valid) {
           if (p.out16) {
