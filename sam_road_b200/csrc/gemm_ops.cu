@@ -63,14 +63,14 @@ int gemm_f32out(const __half* A, int lda, const __half* W, int ldw, int M, int N
 int gemm_ln(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K,
             const float* bias, const float* resid, const float* gamma, const float* beta, float eps,
             int group, int act, __half* out16, float* out32, float* out_nchw, int tokens, int ldo,
-            cudaStream_t st) {
+            cudaStream_t st, int conv_s) {
   SRB_REQUIRE(group == 64 || group == 128 || group == 256, "gemm_ln: group=%d must be 64, 128 or 256", group);
   SRB_REQUIRE(N % group == 0, "gemm_ln: N=%d not a multiple of group=%d", N, group);
   EpiLN::Params p{out16, out32, out_nchw, bias, resid, gamma, beta, eps, ldo, group, act,
                   tokens > 0 ? tokens : 1, N};
   if (group == 256 || use_bn256(M, N))
-    return launch_gemm_tc<256, 3, EpiLN>(A, lda, W, ldw, M, N, K, p, st);
-  return launch_gemm_tc<128, 5, EpiLN>(A, lda, W, ldw, M, N, K, p, st);
+    return launch_gemm_tc<256, 3, EpiLN>(A, lda, W, ldw, M, N, K, p, st, conv_s);
+  return launch_gemm_tc<128, 5, EpiLN>(A, lda, W, ldw, M, N, K, p, st, conv_s);
 }
 
 int gemm_dec_final(const __half* A, int lda, const __half* W, int ldw, int M, int K,

@@ -449,7 +449,11 @@ struct GemmSmem {
 template <int BN, int STAGES, class Epi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               int M, int N, int K, const __grid_constant__ typename Epi::Params ep) {
+               int M, int N, int K, const __grid_constant__ typename Epi::Params ep, int conv_s) {
+  // conv_s > 0: implicit 3x3 / pad 1 convolution over an NHWC fp16 image [B, conv_s, conv_s, C] (tmA
+  // is then its 4-D map with box {64 ch, conv_s, 128/conv_s, 1}): row m is a pixel, K = 9*C is
+  // ordered (tap, channel) and k-block kb reads the channel block of the tap-shifted 128-pixel slab;
+  // out-of-image taps arrive as TMA zero fill.  (neck conv, image_encoder.py:96-103)
   using SM = GemmSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -500,7 +504,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* sa = smem + stage * SM::kStageBytes;
           uint8_t* sb = sa + SM::kABytes;
           mbar_arrive_expect_tx(&full_bar[stage], SM::kStageBytes);
-          tma_load_2d(sa, &tmA, &full_bar[stage], kb * kGemmBK, m_blk * kGemmBM);
+          if (conv_s > 0) {
+            const int cbs = K / (9 * kGemmBK);           // channel blocks per tap
+            const int tap = kb / cbs, cb = kb - tap * cbs;
+            const int tok0 = m_blk * kGemmBM, ss = conv_s * conv_s;
+            const int b = tok0 / ss, y0 = (tok0 - b * ss) / conv_s;
+            tma_load_4d(sa, &tmA, &full_bar[stage], cb * kGemmBK, tap % 3 - 1, y0 + tap / 3 - 1, b);
+          } else {
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * kGemmBK, m_blk * kGemmBM);
+          }
           tma_load_2d(sb, &tmB, &full_bar[stage], kb * kGemmBK, n_blk * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -583,14 +595,28 @@ int device_sm_count();
 
 template <int BN, int STAGES, class Epi>
 int launch_gemm_tc(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K,
-                   const typename Epi::Params& ep, cudaStream_t stream) {
+                   const typename Epi::Params& ep, cudaStream_t stream, int conv_s = 0) {
   using SM = GemmSmem<BN, STAGES>;
   SRB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   SRB_REQUIRE(N % 32 == 0, "gemm: N=%d must be a multiple of 32", N);
   SRB_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0,
               "gemm: K/lda/ldw (%d/%d/%d) must be multiples of 8", K, lda, ldw);
   CUtensorMap tmA, tmB;
-  if (int rc = make_tmap_f16_2d(&tmA, A, M, K, lda, kGemmBM)) return rc;
+  if (conv_s > 0) {
+    // A = NHWC image [M / conv_s^2, conv_s, conv_s, C = lda]
+    const int C = lda;
+    SRB_REQUIRE(K == 9 * C && C % kGemmBK == 0 && kGemmBM % conv_s == 0 && (conv_s * conv_s) % kGemmBM == 0 &&
+                    M % (conv_s * conv_s) == 0,
+                "gemm conv3x3: unsupported shape M=%d K=%d C=%d s=%d", M, K, C, conv_s);
+    const uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(conv_s),
+                              static_cast<uint64_t>(conv_s), static_cast<uint64_t>(M / (conv_s * conv_s))};
+    const uint64_t strides[3] = {static_cast<uint64_t>(C), static_cast<uint64_t>(conv_s) * C,
+                                 static_cast<uint64_t>(conv_s) * conv_s * C};
+    const uint32_t box[4] = {kGemmBK, static_cast<uint32_t>(conv_s), static_cast<uint32_t>(kGemmBM / conv_s), 1};
+    if (int rc = make_tmap_f16_4d(&tmA, A, dims, strides, box)) return rc;
+  } else {
+    if (int rc = make_tmap_f16_2d(&tmA, A, M, K, lda, kGemmBM)) return rc;
+  }
   if (int rc = make_tmap_f16_2d(&tmB, W, N, K, ldw, BN)) return rc;
   auto kern = gemm_tc_kernel<BN, STAGES, Epi>;
   static bool attr_set = false;   // per template instantiation
@@ -600,7 +626,7 @@ int launch_gemm_tc(const __half* A, int lda, const __half* W, int ldw, int M, in
   }
   const int num_tiles = ((M + kGemmBM - 1) / kGemmBM) * ((N + BN - 1) / BN);
   const int grid = num_tiles < device_sm_count() ? num_tiles : device_sm_count();
-  kern<<<grid, kGemmThreads, SM::kTotal, stream>>>(tmA, tmB, M, N, K, ep);
+  kern<<<grid, kGemmThreads, SM::kTotal, stream>>>(tmA, tmB, M, N, K, ep, conv_s);
   SRB_CUDA_OK(cudaGetLastError());
   note_launch(1);
   return 0;

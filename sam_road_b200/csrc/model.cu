@@ -757,11 +757,19 @@ extern "C" int samroad_encode_masks(samroad_handle_t h, const void* rgb, int rgb
   SRB_T(KT_NECK, 2 * Md * 256 * Dd, Md * Dd * 2 + Md * 256 * 2,
         gemm_ln(w.XN, D, h->neck0_w, D, M, 256, D, nullptr, nullptr, h->neck1_g, h->neck1_b, 1e-6f,
                 256, ACT_NONE, w.N1, nullptr, nullptr, T, 256, st));
-  __half* IM2 = w.H;
-  SRB_T(KT_NECK, 0, Md * 256 * 2 * 10, im2col_3x3(w.N1, B, s, 256, IM2, st));
-  SRB_T(KT_NECK, 2 * Md * 256 * 2304, Md * 2304 * 2 + Md * 256 * 6,
-        gemm_ln(IM2, 2304, h->neck2_w, 2304, M, 256, 2304, nullptr, nullptr, h->neck3_g, h->neck3_b,
-                1e-6f, 256, ACT_NONE, w.FEAT, nullptr, image_embeddings, T, 256, st));
+  if (128 % s == 0 && T % 128 == 0) {
+    // 3x3 conv as an implicit GEMM: the TMA producer reads the nine tap-shifted slabs of the NHWC
+    // tensor directly (zero fill outside the image), no im2col buffer
+    SRB_T(KT_NECK, 2 * Md * 256 * 2304, Md * 256 * 2 * 9 + Md * 256 * 6,
+          gemm_ln(w.N1, 256, h->neck2_w, 2304, M, 256, 2304, nullptr, nullptr, h->neck3_g, h->neck3_b,
+                  1e-6f, 256, ACT_NONE, w.FEAT, nullptr, image_embeddings, T, 256, st, s));
+  } else {
+    __half* IM2 = w.H;
+    SRB_T(KT_NECK, 0, Md * 256 * 2 * 10, im2col_3x3(w.N1, B, s, 256, IM2, st));
+    SRB_T(KT_NECK, 2 * Md * 256 * 2304, Md * 2304 * 2 + Md * 256 * 6,
+          gemm_ln(IM2, 2304, h->neck2_w, 2304, M, 256, 2304, nullptr, nullptr, h->neck3_g, h->neck3_b,
+                  1e-6f, 256, ACT_NONE, w.FEAT, nullptr, image_embeddings, T, 256, st));
+  }
 
   // naive map decoder (model.py:286-295, 490-491) as three GEMMs, pixel shuffle by row indexing
   if (h->hook_after_neck) SRB_CUDA_OK(cudaEventRecord(h->ev_emb, st));   // embeddings are final here

@@ -34,7 +34,7 @@ int gemm_f32out(const __half* A, int lda, const __half* W, int ldw, int M, int N
 int gemm_ln(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K,
             const float* bias, const float* resid, const float* gamma, const float* beta, float eps,
             int group, int act, __half* out16, float* out32, float* out_nchw, int tokens, int ldo,
-            cudaStream_t st);
+            cudaStream_t st, int conv_s = 0);   // conv_s > 0: A is an NHWC image, implicit 3x3 / pad 1 conv
 int gemm_dec_final(const __half* A, int lda, const __half* W, int ldw, int M, int K,
                    const float* bias3, const float* w4, const float* bias4, int s, int P,
                    float* scores, float* logits, cudaStream_t st);
