@@ -143,6 +143,27 @@ def test_toponet_versions(topo):
     assert _maxabs(ts, o_ts) <= TOL_LOGIT
 
 
+def test_toponet_dense_c4():
+    """BASELINE config 4 (toponet_vitb_512_cityscale_8x8): dense TopoNet path -- 1024 keypoints per 512
+    tile, every one of them a query with 16 neighbour slots (16 384 sequences of 16 per tile), ragged
+    validity as inferencer.py:156-176 builds it.  Fused tcgen05 kernel against the oracle."""
+    cfg = _config(512)
+    spec, sd, net = _build(cfg, seed=5)
+    g = torch.Generator().manual_seed(12)
+    feat = torch.randn(2, 256, 32, 32, generator=g).to(DEV)
+    pts, prs, val = [t.to(DEV) for t in synth.make_topo_inputs(2, 512, 1024, seed=13)]
+    assert prs.shape == (2, 1024, 16, 2)
+    with torch.no_grad():
+        o_ts, o_tl = O.infer_toponet(sd, spec, feat, pts, prs, val, return_logits=True)
+    ts = net.infer_toponet(feat, pts, prs, val)
+    v = val.unsqueeze(-1)
+    err_valid = ((ts - o_ts).abs() * v).max().item()
+    _REPORT["toponet_dense_c4"] = {"topo_score_maxabs_valid": err_valid, "sequences": int(2 * 1024),
+                                   "valid_fraction": float(val.float().mean().item())}
+    assert err_valid <= TOL_LOGIT
+    assert _maxabs(ts, o_ts) <= 3 * TOL_LOGIT
+
+
 def test_toponet_edge_cases():
     """float32 / int32 inputs, all-invalid rows (flipped to valid, model.py:128-130), border points
     x = P (legal: the rtree box query is inclusive), empty batch."""
