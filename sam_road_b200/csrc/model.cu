@@ -858,10 +858,12 @@ extern "C" int samroad_toponet(samroad_handle_t h, const float* image_embeddings
         gemm_f32out(w.PF16, 128, h->tp_st_w, 128, pts, 256, 128, nullptr, nullptr, nullptr, 0, w.PST,
                     256, st));
   SRB_T(KT_TOPO_PAIR, 0, tokd * 2, topo_fix_valid(valid, rows, Np, w.VF, st));
-  SRB_T(KT_TOPO_PAIR, tokd * 128 * 6, tokd * 128 * (8 + 6),
-        topo_pair_features(w.PST, h->tp_off_w, h->tp_pair_b, points, pts_dtype, pairs, pairs_dtype, B,
-                           N, Ns, Np, zero_off, w.X32, w.X16, st));
-  if (!no_tf && Np == 16) {
+  const bool fused = !no_tf && Np == 16;
+  if (!fused)
+    SRB_T(KT_TOPO_PAIR, tokd * 128 * 6, tokd * 128 * (8 + 6),
+          topo_pair_features(w.PST, h->tp_off_w, h->tp_pair_b, points, pts_dtype, pairs, pairs_dtype, B,
+                             N, Ns, Np, zero_off, w.X32, w.X16, st));
+  if (fused) {
     // all three encoder layers + output_proj in one persistent tcgen05 kernel
     TopoFusedParams fp;
     for (int l = 0; l < 3; ++l) {
@@ -870,10 +872,11 @@ extern "C" int samroad_toponet(samroad_handle_t h, const float* image_embeddings
       fp.n1_g[l] = t.n1_g; fp.n1_b[l] = t.n1_b; fp.n2_g[l] = t.n2_g; fp.n2_b[l] = t.n2_b;
     }
     fp.out_w = h->tp_out_w; fp.out_b_final = h->tp_out_b;
-    SRB_T(KT_TOPO_GEMM, tokd * 2 * 128 * (384 + 128 * 3) * 3 + tokd * 4 * 16 * 128 * 3,
-          tokd * 128 * 6 + tokd * 8,
-          topo_transformer_fused(w.X32, w.X16, h->tp_chunks, fp, w.VF, tok, topo_logits, topo_scores,
-                                 st));
+    TopoPairInputs pin{w.PST, h->tp_off_w, h->tp_pair_b, points, pairs, pts_dtype, pairs_dtype, N,
+                       Ns * Np, zero_off};
+    SRB_T(KT_TOPO_GEMM, tokd * 2 * 128 * (384 + 128 * 3) * 3 + tokd * 4 * 16 * 128 * 3 + tokd * 128 * 6,
+          tokd * 1024 * 2 + tokd * 8,
+          topo_transformer_fused(pin, h->tp_chunks, fp, w.VF, tok, topo_logits, topo_scores, st));
     return 0;
   }
   if (!no_tf) {

@@ -89,9 +89,17 @@ struct TopoFusedParams {
   const float* out_w;        // [128]
   const float* out_b_final;  // [1]
 };
-int topo_transformer_fused(const float* x32, const __half* x16, const __half* w_chunks,
-                           const TopoFusedParams& fp, const uint8_t* valid_fixed, int tokens,
-                           float* logits, float* scores, cudaStream_t st);
+struct TopoPairInputs {       // what topo_pair_features reads; the fused kernel forms x itself
+  const float* pst;          // [B*N, 256] per-point projections (Ws f | Wt f)
+  const float* w_off;        // [128][2]
+  const float* bias;         // [128]
+  const void* points;        // [B, N, 2]
+  const void* pairs;         // [B, Ns, Np, 2]
+  int pts_dtype, pairs_dtype, N, tokens_per_b, zero_offset;
+};
+int topo_transformer_fused(const TopoPairInputs& in, const __half* w_chunks, const TopoFusedParams& fp,
+                           const uint8_t* valid_fixed, int tokens, float* logits, float* scores,
+                           cudaStream_t st);
 
 // ---- SAM mask-decoder path (sam_decoder.cu), USE_SAM_DECODER: True --------------------------------
 struct SamAttnW { const float *qw, *qb, *kw, *kb, *vw, *vb, *ow, *ob; };

@@ -241,16 +241,16 @@ int topo_output(const float* x32, const uint8_t* valid_fixed, const float* w, co
 }
 
 // ------------------------------------------------------------------------------------------------
-// fused transformer launcher (n_pairs == 16): x32/x16 [tokens,128] from topo_pair_features,
-// weights = 18 chunks [128x128] fp16 in consumption order (per layer: Wq, Wk, Wv, Wo, W1, W2)
+// fused transformer launcher (n_pairs == 16): pair features are formed in the kernel from the
+// per-point projections pst; weights = 18 chunks [128x128] fp16 in consumption order (per layer:
+// Wq, Wk, Wv, Wo, W1, W2)
 // ------------------------------------------------------------------------------------------------
-int topo_transformer_fused(const float* x32, const __half* x16, const __half* w_chunks,
-                           const TopoFusedParams& fp, const uint8_t* valid_fixed, int tokens,
-                           float* logits, float* scores, cudaStream_t st) {
+int topo_transformer_fused(const TopoPairInputs& in, const __half* w_chunks, const TopoFusedParams& fp,
+                           const uint8_t* valid_fixed, int tokens, float* logits, float* scores,
+                           cudaStream_t st) {
   if (tokens <= 0) return 0;
-  CUtensorMap tmX16, tmX32, tmW;
-  if (int rc = make_tmap_f16_2d(&tmX16, x16, tokens, 128, 128, 128)) return rc;
-  if (int rc = make_tmap_f32_2d(&tmX32, x32, tokens, 128, 128, 128)) return rc;
+  SRB_REQUIRE(in.pairs_dtype == 1 || in.pairs_dtype == 2, "topo fused: pairs dtype %d", in.pairs_dtype);
+  CUtensorMap tmW;
   if (int rc = make_tmap_f16_2d(&tmW, w_chunks, 18 * 128, 128, 128, 128)) return rc;
   static bool attr_set = false;
   if (!attr_set) {
@@ -265,11 +265,14 @@ int topo_transformer_fused(const float* x32, const __half* x16, const __half* w_
     p.layer[l].n1_g = fp.n1_g[l]; p.layer[l].n1_b = fp.n1_b[l];
     p.layer[l].n2_g = fp.n2_g[l]; p.layer[l].n2_b = fp.n2_b[l];
   }
+  p.pst = in.pst; p.w_off = in.w_off; p.pair_b = in.bias; p.points = in.points; p.pairs = in.pairs;
+  p.pts_dtype = in.pts_dtype; p.pairs_dtype = in.pairs_dtype; p.N = in.N;
+  p.tokens_per_b = in.tokens_per_b; p.zero_offset = in.zero_offset;
   p.valid = valid_fixed; p.out_w = fp.out_w; p.out_b = fp.out_b_final;
   p.logits = logits; p.scores = scores; p.tokens = tokens;
   p.num_tiles = (tokens + 127) / 128;
   const int grid = p.num_tiles < device_sm_count() ? p.num_tiles : device_sm_count();
-  toponet_tc_kernel<<<grid, kTtcThreads, kTtcSmemBytes, st>>>(tmX16, tmX32, tmW, p);
+  toponet_tc_kernel<<<grid, kTtcThreads, kTtcSmemBytes, st>>>(tmW, p);
   SRB_CUDA_OK(cudaGetLastError());
   note_launch();
   return 0;

@@ -9,7 +9,7 @@
 //   TMEM  cols [0,384)   GEMM accumulators (q|k|v, later out_proj / lin1 / lin2 in [0,128))
 //         cols [384,512) the fp32 residual stream x of the tile (one token per lane)
 //   smem  A buffer 32 KB  current fp16 GEMM A operand (x -> attention output -> x' -> hidden -> x'')
-//         KV buffer 66 KB k and v of the tile as fp16 rows (the x fp32 tile lands here by TMA first)
+//         KV buffer 66 KB k and v of the tile as fp16 rows
 //         weight ring 3 x 32 KB  the 18 [128x128] weight chunks streamed by TMA in consumption order
 // Warps: 0 = TMA producer, 1 = MMA issuer + TMEM allocator, 2..9 = 256 token threads, TWO per token
 // (warps w and w+4 share a TMEM lane quarter): epilogues, attention on CUDA cores, LayerNorm,
@@ -46,6 +46,14 @@ struct TtcLayerParams {
 
 struct TtcParams {
   TtcLayerParams layer[3];
+  // pair features (model.py:96-120), computed in the kernel: x = relu(PS[b,src] + PT[b,tgt] +
+  // Wo (pt[tgt] - pt[src]) + bias) with the per-point projections pst [B*N, 256] (Ws f | Wt f)
+  const float* pst;
+  const float* w_off;     // [128][2]
+  const float* pair_b;    // [128]
+  const void* points;     // [B, N, 2] (x, y)
+  const void* pairs;      // [B, Ns, Np, 2] indices into N
+  int pts_dtype, pairs_dtype, N, tokens_per_b, zero_offset;
   const uint8_t* valid;   // [tokens] fixed validity (all-invalid rows already flipped), or null
   const float* out_w;     // [128]
   const float* out_b;     // [1]
@@ -55,13 +63,22 @@ struct TtcParams {
   int num_tiles;
 };
 
+__device__ __forceinline__ float ttc_load_coord(const void* p, int dtype, size_t idx) {
+  if (dtype == 0) return static_cast<const float*>(p)[idx];
+  if (dtype == 1) return static_cast<float>(static_cast<const long long*>(p)[idx]);
+  return static_cast<float>(static_cast<const int*>(p)[idx]);
+}
+__device__ __forceinline__ long long ttc_load_index(const void* p, int dtype, size_t idx) {
+  if (dtype == 1) return static_cast<const long long*>(p)[idx];
+  return static_cast<long long>(static_cast<const int*>(p)[idx]);
+}
+
 __device__ __forceinline__ void named_bar_sync_tokens() {
   asm volatile("bar.sync 1, 256;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(kTtcThreads, 1)
-toponet_tc_kernel(const __grid_constant__ CUtensorMap tmX16, const __grid_constant__ CUtensorMap tmX32,
-                  const __grid_constant__ CUtensorMap tmW, TtcParams p) {
+toponet_tc_kernel(const __grid_constant__ CUtensorMap tmW, TtcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -69,8 +86,6 @@ toponet_tc_kernel(const __grid_constant__ CUtensorMap tmX16, const __grid_consta
   uint8_t* sKV = smem + kTtcOffKV;
   uint8_t* sW = smem + kTtcOffW;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTtcOffBar);
-  uint64_t* x_full = bars + 0;      // TMA: x16 -> A buffer, x32 -> KV buffer
-  uint64_t* a_free = bars + 1;      // MMA commit: last GEMM of the tile retired (A / KV reusable)
   uint64_t* a_ready = bars + 2;     // 256 token threads: new A operand written
   uint64_t* acc_ready = bars + 3;   // MMA commit: GEMM result in TMEM
   uint64_t* w_full = bars + 4;      // [3]
@@ -81,11 +96,7 @@ toponet_tc_kernel(const __grid_constant__ CUtensorMap tmX16, const __grid_consta
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmX16);
-    tma_prefetch_desc(&tmX32);
     tma_prefetch_desc(&tmW);
-    mbar_init(x_full, 1);
-    mbar_init(a_free, 1);
     mbar_init(a_ready, 256);
     mbar_init(acc_ready, 1);
     for (int i = 0; i < kTtcWStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
@@ -100,15 +111,8 @@ toponet_tc_kernel(const __grid_constant__ CUtensorMap tmX16, const __grid_consta
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
-      int ti = 0, wc = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
-        const int row0 = tile * 128;
-        mbar_wait(a_free, (ti & 1) ^ 1u);
-        mbar_arrive_expect_tx(x_full, 32768 + 65536);
-        tma_load_2d(sA, &tmX16, x_full, 0, row0);
-        tma_load_2d(sA + 16384, &tmX16, x_full, 64, row0);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tma_load_2d(sKV + c * 16384, &tmX32, x_full, c * 32, row0);
+      int wc = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         for (int ch = 0; ch < 3 * kTtcChunksPerLayer; ++ch, ++wc) {
           const int st = wc % kTtcWStages;
           mbar_wait(&w_empty[st], ((wc / kTtcWStages) & 1) ^ 1u);
@@ -122,18 +126,15 @@ toponet_tc_kernel(const __grid_constant__ CUtensorMap tmX16, const __grid_consta
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(128, 128);
-      int ti = 0, wc = 0, ac = 0;   // tiles, weight chunks consumed, a_ready completions consumed
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
+      int wc = 0, ac = 0;   // weight chunks consumed, a_ready completions consumed
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         for (int l = 0; l < 3; ++l) {
           for (int gemm = 0; gemm < 4; ++gemm) {          // 0: in_proj (3 chunks), 1: out, 2: lin1, 3: lin2
-            // every GEMM overwrites accumulator columns the token threads read in the previous
-            // step, so each one (except the very first) waits for their a_ready arrival; the first
-            // GEMM of a tile additionally waits for the tile's x16 / x32 TMA
-            if (!(ti == 0 && l == 0 && gemm == 0)) {
-              mbar_wait(a_ready, ac & 1);
-              ++ac;
-            }
-            if (l == 0 && gemm == 0) mbar_wait(x_full, ti & 1);
+            // every GEMM reads an A operand the token threads have just written (the first one of a
+            // tile: the pair features) and overwrites accumulator columns they read in the previous
+            // step: each waits for their a_ready arrival
+            mbar_wait(a_ready, ac & 1);
+            ++ac;
             tc_fence_after_sync();
             const int nch = gemm == 0 ? 3 : 1;
             for (int j = 0; j < nch; ++j, ++wc) {
@@ -152,7 +153,6 @@ toponet_tc_kernel(const __grid_constant__ CUtensorMap tmX16, const __grid_consta
             umma_commit(acc_ready);
           }
         }
-        umma_commit(a_free);
       }
     }
   } else {
@@ -250,6 +250,26 @@ toponet_tc_kernel(const __grid_constant__ CUtensorMap tmX16, const __grid_consta
       return dot;
     };
 
+    // source / target rows and offset of this thread's pair token in tile `t` (index -> address chain
+    // of the gather; issued one tile ahead so that only the pst loads themselves are exposed)
+    float nx_ox = 0.f, nx_oy = 0.f;
+    size_t nx_ps = 0, nx_pt = 0;
+    auto pair_lookup = [&](int t) {
+      const long tk = static_cast<long>(t) * 128 + row;
+      nx_ox = nx_oy = 0.f;
+      nx_ps = nx_pt = 0;
+      if (t < p.num_tiles && tk < p.tokens) {
+        const size_t b = static_cast<size_t>(tk) / p.tokens_per_b;
+        nx_ps = b * p.N + ttc_load_index(p.pairs, p.pairs_dtype, static_cast<size_t>(tk) * 2 + 0);
+        nx_pt = b * p.N + ttc_load_index(p.pairs, p.pairs_dtype, static_cast<size_t>(tk) * 2 + 1);
+        if (!p.zero_offset) {
+          nx_ox = ttc_load_coord(p.points, p.pts_dtype, nx_pt * 2 + 0) -
+                  ttc_load_coord(p.points, p.pts_dtype, nx_ps * 2 + 0);
+          nx_oy = ttc_load_coord(p.points, p.pts_dtype, nx_pt * 2 + 1) -
+                  ttc_load_coord(p.points, p.pts_dtype, nx_ps * 2 + 1);
+        }
+      }
+    };
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
       const long tok = static_cast<long>(tile) * 128 + row;
       const bool tok_ok = tok < p.tokens;
@@ -266,24 +286,41 @@ toponet_tc_kernel(const __grid_constant__ CUtensorMap tmX16, const __grid_consta
         my_valid = tok_ok && p.valid[tok];
       }
 
-      // ---- x (fp32) : smem (TMA, 4 boxes of [128 x 32 floats], 128B swizzle) -> TMEM residual ----
-      mbar_wait(x_full, ti & 1);
+      // ---- pair features of this token -> TMEM residual (fp32) and A buffer (fp16) ----
+      {
+        if (ti == 0) pair_lookup(tile);              // later tiles: looked up during the previous tile
+        const float ox = nx_ox, oy = nx_oy;
+        const size_t ps = nx_ps, pt = nx_pt;
 #pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = part * 2 + cc;
-        float v[32];
-        const uint8_t* src = sKV + c * 16384 + row * 128;
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = part * 2 + cc;
+          float v[32];
+          const float4* a4 = reinterpret_cast<const float4*>(p.pst + ps * 256 + c * 32);
+          const float4* b4 = reinterpret_cast<const float4*>(p.pst + pt * 256 + 128 + c * 32);
+          const float4* w4 = reinterpret_cast<const float4*>(p.w_off + c * 64);
+          const float4* c4 = reinterpret_cast<const float4*>(p.pair_b + c * 32);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 f = *reinterpret_cast<const float4*>(src + ((j ^ sw) << 4));
-          v[4 * j] = f.x; v[4 * j + 1] = f.y; v[4 * j + 2] = f.z; v[4 * j + 3] = f.w;
+          for (int i = 0; i < 8; ++i) {
+            const float4 a = a4[i], bb = b4[i], w0 = __ldg(w4 + 2 * i), w1 = __ldg(w4 + 2 * i + 1),
+                         cb = __ldg(c4 + i);
+            float x0 = a.x + bb.x, x1 = a.y + bb.y, x2 = a.z + bb.z, x3 = a.w + bb.w;
+            x0 += w0.x * ox + w0.y * oy + cb.x;
+            x1 += w0.z * ox + w0.w * oy + cb.y;
+            x2 += w1.x * ox + w1.y * oy + cb.z;
+            x3 += w1.z * ox + w1.w * oy + cb.w;
+            v[4 * i + 0] = tok_ok ? fmaxf(x0, 0.f) : 0.f;
+            v[4 * i + 1] = tok_ok ? fmaxf(x1, 0.f) : 0.f;
+            v[4 * i + 2] = tok_ok ? fmaxf(x2, 0.f) : 0.f;
+            v[4 * i + 3] = tok_ok ? fmaxf(x3, 0.f) : 0.f;
+          }
+          st_chunk(tRes + c * 32, v);
+          write_a_chunk(c, v);
         }
-        st_chunk(tRes + c * 32, v);
+        tmem_st_wait();
+        tc_fence_before_sync();
+        fence_proxy_async_smem();
+        mbar_arrive(a_ready);
       }
-      tmem_st_wait();
-      tc_fence_before_sync();
-      named_bar_sync_tokens();                       // every thread is done with the x32 smem tile
-      tc_fence_after_sync();
 
       float dot = 0.f;
 #pragma unroll 1
@@ -391,13 +428,14 @@ toponet_tc_kernel(const __grid_constant__ CUtensorMap tmX16, const __grid_consta
         tc_fence_before_sync();
         fence_proxy_async_smem();
         mbar_arrive(a_ready);
+        if (l == 2) pair_lookup(tile + static_cast<int>(gridDim.x));   // next tile's indices, off the critical path
         // ================= linear2 + residual + LayerNorm2 =================
         mbar_wait(acc_ready, rc & 1); ++rc;
         tc_fence_after_sync();
         dot = residual_layernorm(L.l2_b, L.n2_g, L.n2_b, l < 2, l == 2 ? p.out_w : nullptr);
         tc_fence_before_sync();
         fence_proxy_async_smem();
-        mbar_arrive(a_ready);     // l == 2: releases the accumulator columns for the next tile
+        if (l < 2) mbar_arrive(a_ready);   // after the last layer the next tile's pair features arrive
       }
       // ================= output_proj + sigmoid =================
       dot = combine(2, dot);
