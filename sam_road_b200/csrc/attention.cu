@@ -14,6 +14,7 @@
 // in chunks of 32 with an online softmax).  It is the straightforward, easily-audited statement of
 // the math and the on-device checker for the tensor-core version.
 #include "attention_tc.cuh"
+#include "attention_tc80.cuh"
 #include "common.cuh"
 #include "ops.h"
 
@@ -204,20 +205,24 @@ static int launch_attention_simt(const __half* qkv, const float* qkv_bias, const
 // rel_pos_w[r - rows/2] for rows/2 <= r < rows/2 + 2K-1, 0 otherwise; fp16 [rows, 64]
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_rel_table_kernel(const float* __restrict__ rel_h, const float* __restrict__ rel_w,
-                                      int win, int hd, int rows, __half* __restrict__ tab) {
+                                      int win, int hd, int ld, int rows, __half* __restrict__ tab) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows * hd) return;
-  const int r = idx / hd, c = idx % hd, L = 2 * win - 1;
+  if (idx >= rows * ld) return;
+  const int r = idx / ld, c = idx % ld, L = 2 * win - 1;
   float v = 0.f;
-  if (r < L) v = rel_h[r * hd + c];
-  else if (r >= rows / 2 && r < rows / 2 + L) v = rel_w[(r - rows / 2) * hd + c];
+  if (c < hd) {
+    if (r < L) v = rel_h[r * hd + c];
+    else if (r >= rows / 2 && r < rows / 2 + L) v = rel_w[(r - rows / 2) * hd + c];
+  }
   tab[idx] = __float2half_rn(v);
 }
 
+// fp16 [rows, ld] with ld = 64 (head_dim 64) or 128 (head_dim 80, columns 80.. zero)
 int pack_rel_table(const float* rel_h, const float* rel_w, int win, int hd, __half* tab,
                    cudaStream_t st) {
   const int rows = rel_table_rows(win);
-  pack_rel_table_kernel<<<(rows * hd + 255) / 256, 256, 0, st>>>(rel_h, rel_w, win, hd, rows, tab);
+  const int ld = hd == 64 ? 64 : 128;
+  pack_rel_table_kernel<<<(rows * ld + 255) / 256, 256, 0, st>>>(rel_h, rel_w, win, hd, ld, rows, tab);
   SRB_CUDA_OK(cudaGetLastError());
   note_launch();
   return 0;
@@ -275,6 +280,44 @@ static int launch_attention_tc(const __half* qkv, const float* qkv_bias, const _
   return 0;
 }
 
+template <bool kWindow, int WIN>
+static int launch_attention_tc80(const __half* qkv, const float* qkv_bias, const __half* tab, int B,
+                                 int s, int heads, __half* out, cudaStream_t st) {
+  const int D = heads * kAtc80HD;
+  const int T = s * s;
+  using SM = Atc80Smem<kWindow, WIN>;
+  CUtensorMap tmQKV, tmTab;
+  if (kWindow) {
+    const uint64_t dims[4] = {static_cast<uint64_t>(3 * D), static_cast<uint64_t>(s),
+                              static_cast<uint64_t>(s), static_cast<uint64_t>(B)};
+    const uint64_t strides[3] = {static_cast<uint64_t>(3 * D), static_cast<uint64_t>(s) * 3 * D,
+                                 static_cast<uint64_t>(T) * 3 * D};
+    const uint32_t box[4] = {64, static_cast<uint32_t>(WIN), static_cast<uint32_t>(WIN), 1};
+    if (int rc = make_tmap_f16_4d(&tmQKV, qkv, dims, strides, box)) return rc;
+  } else {
+    if (int rc = make_tmap_f16_2d(&tmQKV, qkv, static_cast<uint64_t>(B) * T, 3 * D, 3 * D, 128))
+      return rc;
+  }
+  if (int rc = make_tmap_f16_2d(&tmTab, tab, SM::NTAB, 128, 128, SM::NTAB)) return rc;
+  auto kern = attention_tc80_kernel<kWindow, WIN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
+    attr_set = true;
+  }
+  AtcParams p;
+  p.qkv_bias = qkv_bias; p.out = out; p.B = B; p.s = s; p.heads = heads; p.D = D;
+  p.nwin = kWindow ? (s + WIN - 1) / WIN : 1;
+  p.scale_log2e = 0.11180339887498948f * 1.4426950408889634f;      // 80^-0.5 * log2(e)
+  p.num_units = kWindow ? B * p.nwin * p.nwin * heads : B * (T / 128) * heads;
+  p.trace = nullptr; p.no_stagger = 1; p.alternate = 0;
+  const int grid = p.num_units < device_sm_count() ? p.num_units : device_sm_count();
+  kern<<<grid, kAtc80Threads, SM::kBytes, st>>>(tmQKV, tmTab, p);
+  SRB_CUDA_OK(cudaGetLastError());
+  note_launch();
+  return 0;
+}
+
 int encoder_attention(const __half* qkv, const float* qkv_bias, const float* rel_h,
                       const float* rel_w, const __half* rel_tab, int B, int s, int win, int heads,
                       int hd, __half* out, cudaStream_t st) {
@@ -294,6 +337,21 @@ int encoder_attention(const __half* qkv, const float* qkv_bias, const float* rel
     if (win == 14 && win < s) return launch_attention_tc<true, 14>(qkv, qkv_bias, tab, B, s, heads, out, st);
     if (s == 16) return launch_attention_tc<false, 16>(qkv, qkv_bias, tab, B, s, heads, out, st);
     return launch_attention_tc<false, 32>(qkv, qkv_bias, tab, B, s, heads, out, st);
+  }
+  // head_dim 80 (ViT-H): tensor-core kernel with two K-blocks per operand tile
+  const bool tc80_ok = hd == 80 && !g_force_simt &&
+                       ((win == 14 && s >= 14) || (win == s && (s == 16 || s == 32)));
+  if (tc80_ok) {
+    const __half* tab = rel_tab;
+    if (!tab) {
+      static __half* scratch80 = nullptr;
+      if (!scratch80) SRB_CUDA_OK(cudaMalloc(&scratch80, 128 * 128 * sizeof(__half)));
+      SRB_TRY_RC(pack_rel_table(rel_h, rel_w, win, hd, scratch80, st));
+      tab = scratch80;
+    }
+    if (win == 14 && win < s) return launch_attention_tc80<true, 14>(qkv, qkv_bias, tab, B, s, heads, out, st);
+    if (s == 16) return launch_attention_tc80<false, 16>(qkv, qkv_bias, tab, B, s, heads, out, st);
+    return launch_attention_tc80<false, 32>(qkv, qkv_bias, tab, B, s, heads, out, st);
   }
   if (hd == 64) return launch_attention_simt<64>(qkv, qkv_bias, rel_h, rel_w, B, s, win, heads, out, st);
   if (hd == 80) return launch_attention_simt<80>(qkv, qkv_bias, rel_h, rel_w, B, s, win, heads, out, st);

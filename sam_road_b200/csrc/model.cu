@@ -488,9 +488,9 @@ extern "C" int samroad_finalize_weights(samroad_handle_t h) {
     b.rel_h = P.f32(K("attn.rel_pos_h"), {rel_rows, hd});
     b.rel_w = P.f32(K("attn.rel_pos_w"), {rel_rows, hd});
     b.rel_tab = nullptr;
-    if (P.ok && hd == 64) {   // [rows, 64] fp16 table consumed by attention_tc_kernel
+    if (P.ok && (hd == 64 || hd == 80)) {   // fp16 table [rows, 64 | 128] of the tensor-core attention
       void* d = nullptr;
-      if (cudaMalloc(&d, 128 * 64 * sizeof(__half)) != cudaSuccess) {
+      if (cudaMalloc(&d, 128 * 128 * sizeof(__half)) != cudaSuccess) {
         P.fail("cudaMalloc of rel-pos table failed");
       } else {
         h->weight_allocs.push_back(d);

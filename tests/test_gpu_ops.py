@@ -209,7 +209,8 @@ def test_layernorm(M, D):
 
 @pytest.mark.parametrize("B,s,win,heads,hd", [(2, 16, 14, 12, 64), (2, 16, 16, 12, 64),
                                               (1, 32, 14, 12, 64), (1, 32, 32, 12, 64),
-                                              (1, 16, 14, 16, 80), (1, 16, 16, 16, 80)])
+                                              (1, 16, 14, 16, 80), (1, 16, 16, 16, 80),
+                                              (2, 32, 14, 16, 80), (1, 32, 32, 16, 80)])
 def test_encoder_attention(B, s, win, heads, hd):
     """Window (pad-after-LN semantics) and global attention with decomposed rel-pos."""
     lib = _lib.load()
@@ -247,11 +248,13 @@ def test_encoder_attention(B, s, win, heads, hd):
     assert err < tol, (err, tol)
 
 
-@pytest.mark.parametrize("B,s,win", [(3, 32, 14), (3, 32, 32), (5, 16, 14), (5, 16, 16)])
-def test_attention_tc_vs_simt(B, s, win):
-    """tcgen05 kernel against the fp32 SIMT kernel on identical inputs (independent checker)."""
+@pytest.mark.parametrize("B,s,win,heads,hd", [(3, 32, 14, 12, 64), (3, 32, 32, 12, 64), (5, 16, 14, 12, 64),
+                                              (5, 16, 16, 12, 64), (12, 16, 14, 16, 80), (12, 16, 16, 16, 80),
+                                              (3, 32, 14, 16, 80), (2, 32, 32, 16, 80)])
+def test_attention_tc_vs_simt(B, s, win, heads, hd):
+    """tcgen05 kernels (head_dim 64 and 80) against the fp32 SIMT kernel on identical inputs
+    (independent checker); batches large enough that every CTA runs several units."""
     lib = _lib.load()
-    heads, hd = 12, 64
     D = heads * hd
     g = torch.Generator().manual_seed(11)
     qkv16 = (torch.randn(B * s * s, 3 * D, generator=g) * 1.5).to(torch.float16).to(DEV)

@@ -56,7 +56,7 @@ def main():
     a = ap.parse_args()
     out = [run("vitb_256 (C1/C3 tile shape) + TopoNet 64 keypoints", cfg(256), 256, 64, a.steps),
            run("vitb_512 dense TopoNet (C4: 1024 keypoints x 16 pairs)", cfg(512), 64, 1024, a.steps),
-           run("vith_256 encoder + mask head (C5; attention on the fp32 SIMT kernel, head_dim 80)",
+           run("vith_256 encoder + mask head (C5; head_dim 80 tcgen05 attention)",
                cfg(256, "vit_h"), 64, 0, a.steps)]
     print(json.dumps(out, indent=1))
 
