@@ -261,6 +261,8 @@ def run_native(args):
     for i in range(args.warmup):
         step(i)
     barrier()
+    if args.debug_gemm_mode:
+        lib.samroad_debug_disable_2cta_gemm(args.debug_gemm_mode)
     handle = net._handle(dev)
     _lib.check(lib.samroad_timing_enable(handle, 1), "timing_enable")
     lib.samroad_launch_count(1)
@@ -425,6 +427,8 @@ def main():
     ap.add_argument("--ref-tiles", type=int, default=4,
                     help="tiles per step of the CPU reference arm (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--debug-gemm-mode", type=int, default=0,
+                    help="A/B only: samroad_debug_disable_2cta_gemm bit mask (16 = no snake traversal)")
     args = ap.parse_args()
     with _JsonStdout() as out:
         _OUT = out

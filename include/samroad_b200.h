@@ -153,7 +153,8 @@ void samroad_debug_force_simt_attention(int on);
 /* Test hook (bit mask): bit 0 routes every GEMM through the 1-CTA kernels (the 2-CTA cta_group::2
  * kernel is then checked against them); bit 1 routes the in-place fp32 shortcut GEMMs through the
  * register-path epilogue instead of the TMA one; bit 2 selects the TMA load+store variant of that
- * epilogue (bit-identical to the register path) instead of the default TMA reduce-add. */
+ * epilogue (bit-identical to the register path) instead of the default TMA reduce-add; bit 4 makes
+ * every encoder kernel walk the token rows in ascending order (no snake traversal). */
 void samroad_debug_disable_2cta_gemm(int off);
 /* Debug hook: device buffer of 256 int64 receiving clock64 stamps of CTA 0's first work unit in the
  * tcgen05 attention kernel (softmax warp phases, MMA issue times); NULL disables. */

@@ -273,6 +273,7 @@ static int launch_attention_tc(const __half* qkv, const float* qkv_bias, const _
   p.trace = g_att_trace;
   p.no_stagger = g_no_stagger ? 1 : 0;
   p.alternate = g_alternate ? 1 : 0;
+  p.reverse = traverse_reverse() ? 1 : 0;
   const int grid = units < device_sm_count() ? units : device_sm_count();   // persistent CTAs
   kern<<<grid, kAtcThreads, AtcSmem<kWindow>::kBytes, st>>>(tmQKV, tmTab, p);
   SRB_CUDA_OK(cudaGetLastError());
@@ -310,7 +311,7 @@ static int launch_attention_tc80(const __half* qkv, const float* qkv_bias, const
   p.nwin = kWindow ? (s + WIN - 1) / WIN : 1;
   p.scale_log2e = 0.11180339887498948f * 1.4426950408889634f;      // 80^-0.5 * log2(e)
   p.num_units = kWindow ? B * p.nwin * p.nwin * heads : B * (T / 128) * heads;
-  p.trace = nullptr; p.no_stagger = 1; p.alternate = 0;
+  p.trace = nullptr; p.no_stagger = 1; p.alternate = 0; p.reverse = traverse_reverse() ? 1 : 0;
   const int grid = p.num_units < device_sm_count() ? p.num_units : device_sm_count();
   kern<<<grid, kAtc80Threads, SM::kBytes, st>>>(tmQKV, tmTab, p);
   SRB_CUDA_OK(cudaGetLastError());

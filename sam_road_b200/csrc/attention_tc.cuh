@@ -64,6 +64,7 @@ struct AtcParams {
   float scale_log2e;       // head_dim^-0.5 * log2(e)
   int no_stagger;          // A/B hook: do not delay group 1 by half a block
   int alternate;           // A/B hook: strict alternation of the groups' exponential phases
+  int reverse;             // units in descending order
   long long* trace;        // debug: 256 clock64 stamps of CTA 0 (softmax warp 4: 8 per block; MMA threads; unit phases), or null
 };
 
@@ -74,6 +75,7 @@ struct AtcUnit {
 template <bool kWindow, int WIN>
 __device__ __forceinline__ AtcUnit atc_decode(int u, const AtcParams& p) {
   AtcUnit r;
+  if (p.reverse) u = p.num_units - 1 - u;      // walk the images backwards (set_traverse_reverse)
   r.wy = r.wx = r.slab = 0;
   if constexpr (kWindow) {
     r.head = u % p.heads; u /= p.heads;

@@ -50,6 +50,7 @@ struct Atc80Unit {
 template <bool kWindow, int WIN>
 __device__ __forceinline__ Atc80Unit atc80_decode(int u, const AtcParams& p) {
   Atc80Unit r;
+  if (p.reverse) u = p.num_units - 1 - u;
   r.wy = r.wx = r.slab = 0;
   r.head = u % p.heads; u /= p.heads;
   if constexpr (kWindow) {

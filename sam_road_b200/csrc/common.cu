@@ -139,4 +139,13 @@ int make_tmap_f32_4d_dense(CUtensorMap* out, const void* base, const uint64_t di
   return 0;
 }
 
+// Traversal direction of the next row-streaming kernel (LayerNorm, 2-CTA GEMMs, encoder attention):
+// the encoder alternates it from kernel to kernel so that each kernel starts on the rows its
+// producer wrote last, i.e. on what is still in the 126 MB L2 (activations are 100-400 MB).
+static bool g_traverse_reverse = false;
+static bool g_traverse_snake_off = false;     // A/B hook
+void set_traverse_snake_enabled(bool on) { g_traverse_snake_off = !on; }
+void set_traverse_reverse(bool r) { g_traverse_reverse = r && !g_traverse_snake_off; }
+bool traverse_reverse() { return g_traverse_reverse; }
+
 }  // namespace srb

@@ -479,6 +479,9 @@ int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
 // 128B swizzle (b0 * 2 bytes must be 128).  Out-of-bounds elements read as zero.
 int make_tmap_f16_4d(CUtensorMap* out, const void* base, const uint64_t dims[4],
                      const uint64_t strides_elems[3], const uint32_t box[4]);
+void set_traverse_reverse(bool r);   // next row-streaming kernel walks its tiles / units / rows backwards
+bool traverse_reverse();
+void set_traverse_snake_enabled(bool on);   // A/B hook: false = every kernel ascending
 int make_tmap_f32_4d_dense(CUtensorMap* out, const void* base, const uint64_t dims[4],
                            const uint64_t strides_bytes[3], const uint32_t box[4]);
 

@@ -66,7 +66,8 @@ __device__ __forceinline__ void epi_f16_pack_chunk(const float (&v)[32], const f
 template <class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmO, int M, int N, int K, typename Epi::Params ep) {
+                const __grid_constant__ CUtensorMap tmO, int M, int N, int K, typename Epi::Params ep,
+                int reverse) {
   using SM = Gemm2Smem;
   constexpr int STAGES = kGemm2Stages;
   constexpr int BN = 256;
@@ -119,7 +120,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        const int tt = reverse ? num_tiles - 1 - tile : tile;
+        const int m_blk = tt / num_n, n_blk = tt % num_n;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * SM::kStageBytes;
@@ -173,7 +175,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int as = 0;
       uint32_t aphase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        const int tt = reverse ? num_tiles - 1 - tile : tile;
+        const int m_blk = tt / num_n, n_blk = tt % num_n;
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after_sync();
         const int m0 = m_blk * 256 + static_cast<int>(rank) * 128 + q * 32;
@@ -263,7 +266,7 @@ int launch_gemm_tc2(const __half* A, int lda, const __half* W, int ldw, int M, i
   const int num_tiles = ((M + 255) / 256) * (N / 256);
   const int max_clusters = device_sm_count() / 2;
   const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
-  kern<<<2 * clusters, kGemmThreads, SM::kTotal, stream>>>(tmA, tmB, tmO, M, N, K, ep);
+  kern<<<2 * clusters, kGemmThreads, SM::kTotal, stream>>>(tmA, tmB, tmO, M, N, K, ep, traverse_reverse() ? 1 : 0);
   SRB_CUDA_OK(cudaGetLastError());
   note_launch(1);
   return 0;

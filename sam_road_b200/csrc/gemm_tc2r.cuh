@@ -31,7 +31,7 @@ template <int STAGES, int NB, bool kReduce>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_tc2_resid_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmR,
-                      int M, int N, int K, const float* __restrict__ bias, int load_rows) {
+                      int M, int N, int K, const float* __restrict__ bias, int load_rows, int reverse) {
   using SM = Gemm2RSmem<STAGES, NB>;
   constexpr int BN = 256;
   extern __shared__ uint8_t smem_raw[];
@@ -85,7 +85,8 @@ gemm_tc2_resid_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        const int tt = reverse ? num_tiles - 1 - tile : tile;
+        const int m_blk = tt / num_n, n_blk = tt % num_n;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * SM::kStageBytes;
@@ -138,7 +139,8 @@ gemm_tc2_resid_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int my_tiles = cluster_id < num_tiles ? (num_tiles - cluster_id + num_clusters - 1) / num_clusters : 0;
     const int total = my_tiles * 4;    // 32x32 blocks this warp streams
     auto coords = [&](int g, int& x, int& y) {
-      const int tile = cluster_id + (g >> 2) * num_clusters;
+      const int tile0 = cluster_id + (g >> 2) * num_clusters;
+      const int tile = reverse ? num_tiles - 1 - tile0 : tile0;
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       y = m_blk * 256 + static_cast<int>(rank) * 128 + q * 32;
       x = n_blk * BN + half * 128 + (g & 3) * 32;
@@ -272,7 +274,8 @@ int launch_gemm_tc2_resid(const __half* A, int lda, const __half* W, int ldw, in
   const int num_tiles = ((M + 255) / 256) * (N / 256);
   const int max_clusters = device_sm_count() / 2;
   const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
-  kern<<<2 * clusters, kGemmThreads, SM::kTotal, stream>>>(tmA, tmB, tmX, tmR, M, N, K, bias, load_rows);
+  kern<<<2 * clusters, kGemmThreads, SM::kTotal, stream>>>(tmA, tmB, tmX, tmR, M, N, K, bias, load_rows,
+                                                           traverse_reverse() ? 1 : 0);
   SRB_CUDA_OK(cudaGetLastError());
   note_launch(1);
   return 0;

@@ -16,8 +16,9 @@ constexpr int kLNMaxVec = 10;
 __global__ void __launch_bounds__(256)
 layernorm_f16_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ beta, float eps, int M, int D,
-                     __half* __restrict__ out) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+                     __half* __restrict__ out, int reverse) {
+  const int blk = reverse ? static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x);
+  const int row = blk * 8 + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
   const int nvec = D >> 7;   // float4 per lane
@@ -61,7 +62,7 @@ int layernorm_f16(const float* x, const float* gamma, const float* beta, float e
                   __half* out, cudaStream_t st) {
   SRB_REQUIRE(D % 128 == 0 && D <= 128 * kLNMaxVec, "layernorm: D=%d unsupported", D);
   if (M <= 0) return 0;
-  layernorm_f16_kernel<<<(M + 7) / 8, 256, 0, st>>>(x, gamma, beta, eps, M, D, out);
+  layernorm_f16_kernel<<<(M + 7) / 8, 256, 0, st>>>(x, gamma, beta, eps, M, D, out, traverse_reverse() ? 1 : 0);
   SRB_CUDA_OK(cudaGetLastError());
   note_launch();
   return 0;

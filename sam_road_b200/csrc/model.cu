@@ -721,7 +721,11 @@ extern "C" int samroad_encode_masks(samroad_handle_t h, const void* rgb, int rgb
   SRB_T(KT_GEMM_PATCH, 2 * Md * Dd * 768, Md * 768 * 2 + Md * Dd * 4,
         gemm_f32out(w.XN, 768, h->pe_w, 768, M, D, 768, h->pe_b, nullptr, h->pos, T, w.X, D, st));
 
-  // transformer blocks (image_encoder.py:166-182)
+  // transformer blocks (image_encoder.py:166-182).  The seven kernels of a block stream the same
+  // M x D token rows; they walk them in alternating directions (snake) so that every kernel starts on
+  // the rows its producer wrote last, which are the ones still in L2.
+  bool snake = true;    // the patch embedding ran ascending
+  auto turn = [&]() { set_traverse_reverse(snake); snake = !snake; };
   for (int i = 0; i < h->cfg.depth; ++i) {
     const BlockW& b = h->blocks[i];
     // algorithmic attention FLOPs: real query/key tokens only
@@ -736,21 +740,30 @@ extern "C" int samroad_encode_masks(samroad_handle_t h, const void* rgb, int rgb
         }
       att_flops *= static_cast<double>(B) * h->cfg.num_heads;
     }
+    turn();
     SRB_T(KT_LAYERNORM, 0, Md * Dd * 6, layernorm_f16(w.X, b.ln1_g, b.ln1_b, 1e-6f, M, D, w.XN, st));
+    turn();
     SRB_T(KT_GEMM_QKV, 2 * Md * 3 * Dd * Dd, Md * Dd * 2 + Md * 3 * Dd * 2,
           gemm_f16out(w.XN, D, b.qkv_w, D, M, 3 * D, D, b.qkv_b, ACT_NONE, w.QKV, 3 * D, st));
+    turn();
     SRB_T(b.win == s ? KT_ATTN_GLOBAL : KT_ATTN_WINDOW, att_flops, Md * 4 * Dd * 2,
           encoder_attention(w.QKV, b.qkv_b, b.rel_h, b.rel_w, b.rel_tab, B, s, b.win,
                             h->cfg.num_heads, h->hd, w.ATT, st));
+    turn();
     SRB_T(KT_GEMM_PROJ, 2 * Md * Dd * Dd, Md * Dd * 2 + Md * Dd * 8,
           gemm_f32out(w.ATT, D, b.proj_w, D, M, D, D, b.proj_b, w.X, nullptr, 0, w.X, D, st));
+    turn();
     SRB_T(KT_LAYERNORM, 0, Md * Dd * 6, layernorm_f16(w.X, b.ln2_g, b.ln2_b, 1e-6f, M, D, w.XN, st));
+    turn();
     SRB_T(KT_GEMM_LIN1, 2 * Md * 4 * Dd * Dd, Md * Dd * 2 + Md * 4 * Dd * 2,
           gemm_f16out(w.XN, D, b.lin1_w, D, M, 4 * D, D, b.lin1_b, ACT_GELU, w.H, 4 * D, st));
+    turn();
     SRB_T(KT_GEMM_LIN2, 2 * Md * 4 * Dd * Dd, Md * 4 * Dd * 2 + Md * Dd * 8,
           gemm_f32out(w.H, 4 * D, b.lin2_w, 4 * D, M, D, 4 * D, b.lin2_b, w.X, nullptr, 0, w.X, D,
                       st));
   }
+
+  set_traverse_reverse(false);
 
   // neck (image_encoder.py:88-104,114): 1x1 conv -> LN2d -> 3x3 conv -> LN2d
   SRB_T(KT_NECK, 0, Md * Dd * 6, convert_f32_f16(w.X, static_cast<long>(M) * D, w.XN, st));
@@ -1061,4 +1074,7 @@ extern "C" int samroad_op_attention(const void* qkv16, const float* qkv_bias, co
 }
 extern "C" void samroad_debug_force_simt_attention(int on) { attention_force_simt(on); }
 extern "C" void samroad_debug_attention_trace(void* dev_buf) { attention_set_trace(static_cast<long long*>(dev_buf)); }
-extern "C" void samroad_debug_disable_2cta_gemm(int off) { gemm_disable_2cta(off); }
+extern "C" void samroad_debug_disable_2cta_gemm(int off) {
+  gemm_disable_2cta(off);
+  set_traverse_snake_enabled((off & 16) == 0);
+}
