@@ -325,11 +325,12 @@ def run_native(args):
 
     # ---- roofline of the dominant kernel class ---------------------------------------------------
     # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernel classes captured
-    # with `ncu --set full` at this workload: profiles/r01_gemm_f16_v3_raw.csv, r01_gemm_resid_v3_raw.csv,
-    # r01_att_v5_raw.csv (tools/gpu/profile_r01.sh).  Only valid for the default batch of 64 tiles.
-    ncu_traffic = {"gemm_mlp_lin1": 105.511168e6 + 345.874176e6, "gemm_qkv": 104.280576e6 + 247.809280e6,
-                   "gemm_mlp_lin2": 613.990144e6 + 170.727168e6, "gemm_proj": 303.192576e6 + 143.959552e6,
-                   "attention_global": 302.227456e6 + 81.448448e6, "attention_window": 302.059520e6 + 78.373376e6}
+    # with `ncu --set full` at this workload: profiles/r01_gemm_f16_v4_raw.csv, r01_gemm_resid_v4_raw.csv
+    # (proj: r01_gemm_resid_v3_raw.csv), r01_att_v6_raw.csv (tools/gpu/profile_r01.sh).  Only valid for
+    # the default batch of 64 tiles.
+    ncu_traffic = {"gemm_mlp_lin1": 105.514240e6 + 347.093760e6, "gemm_qkv": 104.339456e6 + 245.466624e6,
+                   "gemm_mlp_lin2": 614.097152e6 + 172.180992e6, "gemm_proj": 303.192576e6 + 143.959552e6,
+                   "attention_global": 302.231040e6 + 80.478464e6, "attention_window": 302.097664e6 + 78.441216e6}
     peaks = load_peaks()
     gemm_like = {k: v for k, v in kernels.items() if v["flops"] > 0}
     dom = max(gemm_like, key=lambda k: gemm_like[k]["ms"]) if gemm_like else None
@@ -341,7 +342,7 @@ def run_native(args):
         roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"],
                     "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
                     "traffic": ncu_traffic.get(dom) if args.batch == 64 else None,
-                    "traffic_source": "ncu --set full, profiles/r01_*_v3_raw.csv (bytes per launch)",
+                    "traffic_source": "ncu --set full, profiles/r01_*_raw.csv (bytes per launch)",
                     "peak_source": peaks["source"], "launches": d["launches"],
                     "avg_launch_ms": per_launch_ms,
                     "algorithmic_flops_per_launch": d["flops"] / d["launches"]}
