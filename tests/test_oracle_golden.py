@@ -13,8 +13,8 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 TOL = 2e-5
 
 
-def _cfg(patch, topo="normal", lora=0, samdec=False):
-    return dict(SAM_VERSION="vit_b", PATCH_SIZE=patch, USE_SAM_DECODER=samdec, ENCODER_LORA=lora > 0,
+def _cfg(patch, topo="normal", lora=0, samdec=False, version="vit_b"):
+    return dict(SAM_VERSION=version, PATCH_SIZE=patch, USE_SAM_DECODER=samdec, ENCODER_LORA=lora > 0,
                 LORA_RANK=lora, TOPONET_VERSION=topo, NO_SAM=False)
 
 
@@ -24,10 +24,12 @@ def _stats(t):
 
 
 @pytest.mark.parametrize("name,patch,lora", [("vitb_256", 256, 0), ("vitb_512", 512, 0),
-                                             ("vitb_256_lora4", 256, 4), ("vitb_256_samdec", 256, 0)])
+                                             ("vitb_256_lora4", 256, 4), ("vitb_256_samdec", 256, 0),
+                                             ("vith_256", 256, 0)])
 def test_model_against_reference_golden(name, patch, lora):
     g = np.load(os.path.join(GOLD, f"{name}.npz"))
-    cfg = _cfg(patch, lora=lora, samdec=name.endswith("samdec"))
+    cfg = _cfg(patch, lora=lora, samdec=name.endswith("samdec"),
+               version="vit_h" if name.startswith("vith") else "vit_b")
     seed, n_points = int(g["seed"]), int(g["n_points"])
     sd = synth.make_state_dict(cfg, seed=seed)
     spec = O.ModelSpec.from_config(cfg)

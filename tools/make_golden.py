@@ -155,6 +155,7 @@ def main():
     model_fixture("vitb_512", _cfg(512), seed=1, n_points=40)
     model_fixture("vitb_256_lora4", _cfg(256, lora=4), seed=2, n_points=16)
     model_fixture("vitb_256_samdec", _cfg(256, samdec=True), seed=3, n_points=16)
+    model_fixture("vith_256", _cfg(256, version="vit_h"), seed=4, n_points=16)
     toponet_fixture()
     tileloop_fixture()
 
