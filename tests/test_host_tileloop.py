@@ -111,3 +111,18 @@ def test_shard_and_allgather_world2_gloo(n_tiles):
         lo, hi, _ = I._shard(n_tiles, r, 2)
         covered += list(range(lo, hi))
     assert covered == list(range(n_tiles))
+
+
+def test_shard_partitions_every_case():
+    """_shard: contiguous blocks in rank order that partition range(n) for any (n, world), equal
+    `per_rank` on every rank (the all-gather needs equal shard shapes), empty tail shards allowed."""
+    for world in range(1, 10):
+        for n in range(0, 41):
+            covered, pers = [], set()
+            for r in range(world):
+                lo, hi, per = I._shard(n, r, world)
+                assert 0 <= lo <= hi <= n and hi - lo <= per
+                covered += list(range(lo, hi))
+                pers.add(per)
+            assert covered == list(range(n)) and len(pers) == 1
+            assert pers.pop() * world >= n
