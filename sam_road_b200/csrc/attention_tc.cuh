@@ -6,7 +6,8 @@
 //   warp 0        TMA producer: rel-pos table (once), per unit Q (256 rows) and K/V blocks of 128 keys
 //   warp 1        TMEM allocator; lane 0 issues the tcgen05.mma of softmax group 0 (blocking waits)
 //   warp 2        lane 0 issues the tcgen05.mma of softmax group 1
-//   warp 3        idle (completes the control warpgroup, which gives its registers away)
+//   warp 3        window mode: rewrites the K/V rows of window-pad tokens with the qkv bias, one unit
+//                 ahead of the softmax groups (K/V is double-buffered across units); idle otherwise
 //   warps 4-7     softmax group 0 (query rows   0..127 of the unit, one row per thread)
 //   warps 8-11    softmax group 1 (query rows 128..255)
 //
@@ -27,8 +28,13 @@
 // Window mode never materialises window_partition (image_encoder.py:243-264): a 4-D TMA box
 // [64 ch, 14 x, 14 y, 1 img] pulls the window's tokens; out-of-image tokens arrive as zeros and are
 // overwritten in smem with the qkv bias (pad tokens have q=k=v=bias because padding follows norm1,
-// image_encoder.py:168-172).  Their query rows are never stored, and a softmax
-// group whose 128 rows are all padding skips the unit.
+// image_encoder.py:168-172).  Their query rows are never stored; a softmax group
+// whose 128 rows are all padding skips the unit, a warp whose 32 rows are all padding only keeps the
+// barrier protocol moving.
+//
+// TMEM: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384) and, for 64-row rel-pos tables, T0 [384,448)
+// T1 [448,512).  In global mode the two groups take turns on the MUFU (e_done barriers): while one
+// group exponentiates a block the other loads / maximises / stores (tools/att_trace.py: -6 %).
 #pragma once
 
 #include "common.cuh"
