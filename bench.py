@@ -379,6 +379,11 @@ def run_native(args):
         "roofline": roofline,
         "path_tensor_frac": value / world * FLOP_PER_TILE / 1e12 / peaks["tflops"],
         "algorithmic_gflop_per_tile": FLOP_PER_TILE / 1e9,
+        # BASELINE's third metric: sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active of the
+        # dominant kernels from the committed ncu --set full captures (not measured in this run)
+        "tensor_pipe_pct_ncu": {"gemm_qkv": 72.5, "gemm_mlp_lin1": 66.6, "gemm_mlp_lin2": 79.8,
+                                "attention_global": 22.3, "attention_window": 19.2,
+                                "source": "profiles/r01_ncu_summary_v4.md"},
         "kernels": shares,
         "cpu_baseline": cpu,
     }
