@@ -26,12 +26,12 @@
 extern "C" {
 #endif
 
-#define SAMROAD_ABI_VERSION 1
+#define SAMROAD_ABI_VERSION 2
 
 typedef struct samroad_ctx* samroad_handle_t;
 
 /* dtype codes for polymorphic inputs */
-enum { SAMROAD_F32 = 0, SAMROAD_I64 = 1, SAMROAD_I32 = 2, SAMROAD_U8 = 3 };
+enum { SAMROAD_F32 = 0, SAMROAD_I64 = 1, SAMROAD_I32 = 2, SAMROAD_U8 = 3, SAMROAD_F64 = 4 };
 
 /* TOPONET_VERSION (model.py:84,111-116,135).  'no_tgt_features' behaves as 'normal' in the
  * reference because the following if/else overwrites it (model.py:111-116). */
@@ -75,6 +75,13 @@ int samroad_encode_masks(samroad_handle_t h, const void* rgb, int rgb_dtype, int
                          float* mask_scores, float* mask_logits, float* image_embeddings,
                          void* stream);
 
+/* The same for tiles that are windows of a uint8 RGB scene [H,W,3] already on the device: replaces
+ * crop_img_patch / get_batch_img_patches + the per-batch float32 upload (inferencer.py:43-58,87-96).
+ * tile_xy: device int32 [B,2] tile origins (x0,y0); the tile is scene[y0:y0+P, x0:x0+P, :]. */
+int samroad_encode_masks_scene(samroad_handle_t h, const uint8_t* scene, int H, int W,
+                               const int32_t* tile_xy, int B, float* mask_scores, float* mask_logits,
+                               float* image_embeddings, void* stream);
+
 /* SAMRoad.infer_toponet (model.py:498-508) = BilinearSampler (model.py:34-58) + TopoNet.forward
  * (model.py:88-148).  image_embeddings: device fp32 [B,256,s,s]; points [B,N,2] (x,y) pixels,
  * SAMROAD_F32 / I64 / I32; pairs [B,Ns,Np,2] indices into N, SAMROAD_I64 / I32; valid [B,Ns,Np]
@@ -105,6 +112,63 @@ int samroad_infer_batch_host(samroad_handle_t h, const void* rgb_host, int rgb_d
                              int pairs_dtype, const uint8_t* valid_host, int N, int Ns, int Np,
                              float* mask_scores_host, float* image_embeddings_host,
                              float* topo_scores_host);
+
+/* ---- scene graph: the host code between and after the two model passes, on the device ---------- */
+
+typedef struct samroad_graph_ctx* samroad_graph_t;
+
+/* Scratch owner for the three calls below (one per device / scene driver). */
+int samroad_graph_create(int device, samroad_graph_t* out);
+int samroad_graph_destroy(samroad_graph_t g);
+
+/* Optional host callback standing for `numpy.argsort(keys)` (ascending, NumPy's default kind).
+ * keys: n values of key_dtype (SAMROAD_U8 mask scores, SAMROAD_F64 priorities); order_out: n int64.
+ * Returns 0 on success.  graph_utils.nms_points visits candidates in `argsort(scores)[::-1]` order
+ * (graph_utils.py:574); the order of EQUAL scores is an implementation detail of NumPy's unstable
+ * sort (it differs between CPUs), so a caller that needs the reference's exact keypoints on this host
+ * passes NumPy's permutation in; with NULL the device sorts as argsort(kind='stable')[::-1] would. */
+typedef int (*samroad_argsort_fn)(const void* keys, int key_dtype, int64_t n, int64_t* order_out,
+                                  void* user);
+
+/* graph_extraction.extract_graph_points (graph_extraction.py:130-139) including
+ * get_points_and_scores_from_mask (graph_extraction.py:24-28) and the three graph_utils.nms_points
+ * passes (graph_utils.py:572-591: greedy radius NMS in descending score order, inclusive radius,
+ * scores > 1.0 never suppressed).  keypoint_mask / road_mask: device uint8 [H,W] (the fused masks of
+ * inferencer.py:106-110); thresholds are config.*_THRESHOLD * 255 (compared as `mask > thr`).
+ * Output: device int64 [n,2] (x,y) in the reference's order, *n_points on the host.  stats (host,
+ * optional, 8 ints): candidates of the two masks, survivors of passes 1-2, NMS rounds of the three
+ * passes, n.  Synchronises the stream. */
+int samroad_extract_graph_points(samroad_graph_t g, const uint8_t* keypoint_mask,
+                                 const uint8_t* road_mask, int H, int W, double itsc_thr255,
+                                 double road_thr255, double itsc_radius, double road_radius,
+                                 samroad_argsort_fn argsort, void* user, int64_t* points_xy, int cap,
+                                 int* n_points, int32_t* stats, void* stream);
+
+/* Pair-query construction of inferencer.py:126-197 for every tile of the scene: the box query
+ * (rtree.intersection, inclusive bounds, ascending point index) and the per-tile kNN
+ * (KDTree.query(k=MAX_NEIGHBOR_QUERIES+1, distance_upper_bound=NEIGHBOR_RADIUS) minus self: strictly
+ * closer than the radius, ascending distance, equal distances in ascending index).  points_xy: device
+ * int64 [N,2]; tile_xy_host: host int32 [n_tiles,2] tile origins (x0,y0) in tile-list order.
+ * Writes the number of points of every tile to tile_counts_host (the caller pads each batch to its
+ * own maximum, inferencer.py:179-185).  Synchronises the stream. */
+int samroad_pair_queries_plan(samroad_graph_t g, const int64_t* points_xy, int N,
+                              const int32_t* tile_xy_host, int n_tiles, int P, double radius,
+                              int32_t* tile_counts_host, void* stream);
+/* Padded batch tensors for tiles [tile_begin, tile_begin+B): points int32 [B,nmax,2] relative to the
+ * tile origin, pairs int32 [B,nmax,K,2], valid bytes [B,nmax,K] (device) -- the inputs of
+ * samroad_toponet (inferencer.py:164-197).  Asynchronous. */
+int samroad_pair_queries_fill(samroad_graph_t g, int tile_begin, int B, int nmax, int K,
+                              int32_t* points, int32_t* pairs, uint8_t* valid, void* stream);
+
+/* Edge aggregation of inferencer.py:206-230 over the planned tiles: topo_scores is one device fp32
+ * buffer, tile t's scores [nmax_of_its_batch, K] start at element tile_score_offset_host[t] (negative:
+ * the tile's batch was skipped, inferencer.py:188-189).  Per directed (src,tgt) the scores are added in
+ * float32 in (tile, sample, pair) order, averaged and compared with `> threshold`; surviving edges are
+ * written in first-occurrence order as int64 [n,2] global point indices.  *bad_score != 0 when a score
+ * fell outside [0,1] (the reference asserts).  Synchronises the stream. */
+int samroad_aggregate_edges(samroad_graph_t g, const float* topo_scores,
+                            const int64_t* tile_score_offset_host, int K, float threshold,
+                            int64_t* edges, int cap, int* n_edges, int* bad_score, void* stream);
 
 /* Per-kernel-class CUDA-event timing on the launching stream (bench.py's roofline numbers).
  * samroad_timing_enable(h, 1) clears and starts recording; samroad_timing_read() synchronises and

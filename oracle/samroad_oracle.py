@@ -315,14 +315,31 @@ def get_patch_info_one_img(image_index: int, image_size: int, sample_margin: int
     return [(image_index, (x, y), (x + patch_size, y + patch_size)) for x in origins for y in origins]
 
 
-def nms_points(points: np.ndarray, scores: np.ndarray, radius: float) -> np.ndarray:
+def visiting_order(scores: np.ndarray, tie_order: str = "numpy") -> np.ndarray:
+    """`np.argsort(scores)[::-1]` (graph_utils.py:574).  NumPy's default sort is unstable: the order of
+    EQUAL scores is an implementation detail (introsort for uint8, AVX-512 / AVX2 sorting networks for
+    float64 -- different CPUs give different permutations).  tie_order="numpy" is the reference verbatim
+    on this host; tie_order="stable" pins the ties: argsort(kind="stable")[::-1] (descending score,
+    equal scores in descending index) -- the order the device-only sort of csrc/graph.cu produces."""
+    if tie_order == "numpy":
+        return np.argsort(scores)[::-1]
+    assert tie_order == "stable", tie_order
+    return np.argsort(scores, kind="stable")[::-1]
+
+
+def nms_points(points: np.ndarray, scores: np.ndarray, radius: float, tie_order: str = "numpy",
+               shortcut: bool = True) -> np.ndarray:
     """Greedy radius NMS in descending score order; score > 1 is never suppressed
-    (graph_utils.py:572-591)."""
+    (graph_utils.py:572-591).  `shortcut`: when EVERY score is > 1.0 (always the case for mask scores
+    above a threshold >= 1/255) the loop cannot suppress anything and returns the sorted points; the
+    literal loop (shortcut=False) is kept and compared in tests/test_host_tileloop.py."""
     import scipy.spatial
-    order = np.argsort(scores)[::-1]
+    order = visiting_order(scores, tie_order)
     pts, sc = points[order, :], scores[order]
     kept = np.ones(order.shape[0], dtype=bool)
     if pts.shape[0] == 0:
+        return pts
+    if shortcut and bool(np.all(np.greater(sc, 1.0))):
         return pts
     tree = scipy.spatial.KDTree(pts)
     for i, p in enumerate(pts):
@@ -335,23 +352,46 @@ def nms_points(points: np.ndarray, scores: np.ndarray, radius: float) -> np.ndar
 
 
 def extract_graph_points(keypoint_mask: np.ndarray, road_mask: np.ndarray, itsc_thr: float,
-                         road_thr: float, itsc_radius: float, road_radius: float) -> np.ndarray:
+                         road_thr: float, itsc_radius: float, road_radius: float,
+                         tie_order: str = "numpy") -> np.ndarray:
     """graph_extraction.py:24-28,130-139 (thresholds are given in 0..1 and scaled by 255)."""
     def cand(mask, thr):
         rc = np.column_stack(np.where(mask > thr))
         return rc[:, ::-1], mask[mask > thr]
     p0, s0 = cand(keypoint_mask, itsc_thr * 255)
-    k0 = nms_points(p0, s0, itsc_radius)
+    k0 = nms_points(p0, s0, itsc_radius, tie_order)
     p1, s1 = cand(road_mask, road_thr * 255)
-    k1 = nms_points(p1, s1, road_radius)
+    k1 = nms_points(p1, s1, road_radius, tie_order)
     allp = np.concatenate([k0, k1], axis=0)
     alls = np.concatenate([np.ones(k0.shape[0]), np.zeros(k1.shape[0])], axis=0)
-    return nms_points(allp, alls, road_radius)
+    return nms_points(allp, alls, road_radius, tie_order)
 
 
-def build_pair_queries(graph_points: np.ndarray, tile, max_nbr: int, radius: float):
+def knn_by_index(pts: np.ndarray, k: int, radius: float) -> np.ndarray:
+    """`KDTree(pts).query(pts, k=k+1, distance_upper_bound=radius)[1][:, 1:]` (inferencer.py:159-163)
+    with the one thing scipy leaves open pinned: neighbours at EQUAL distance come in ascending index
+    (cKDTree returns them in traversal order).  Strictly closer than `radius` (scipy's upper bound is
+    exclusive), ascending distance, missing slots = n.  Needs distinct points (true after NMS: the
+    nearest neighbour the reference drops is then the point itself)."""
+    n = pts.shape[0]
+    out = np.full((n, k), n, dtype=np.int64)
+    if n == 0:
+        return out
+    p = pts.astype(np.int64)
+    d2 = ((p[:, None, :] - p[None, :, :]) ** 2).sum(-1)
+    np.fill_diagonal(d2, np.iinfo(np.int64).max)
+    lim = float(radius) * float(radius)
+    for i in range(n):
+        cand = np.nonzero(d2[i] < lim)[0]
+        cand = cand[np.lexsort((cand, d2[i, cand]))][:k]
+        out[i, :cand.shape[0]] = cand
+    return out
+
+
+def build_pair_queries(graph_points: np.ndarray, tile, max_nbr: int, radius: float, ties: str = "scipy"):
     """Per-tile pair queries (inferencer.py:148-176).  The rtree box query (inclusive bounds,
-    inferencer.py:150) is restated as a numpy box test with ascending indices."""
+    inferencer.py:150) is restated as a numpy box test with ascending indices.  ties="scipy" is the
+    reference verbatim (cKDTree's order of equidistant neighbours); ties="index" pins it (knn_by_index)."""
     import scipy.spatial
     _, (x0, y0), (x1, y1) = tile
     gx, gy = graph_points[:, 0], graph_points[:, 1]
@@ -360,9 +400,13 @@ def build_pair_queries(graph_points: np.ndarray, tile, max_nbr: int, radius: flo
     pts = graph_points[idx, :] - np.array([[x0, y0]], dtype=graph_points.dtype)
     if n == 0:
         return idx, pts, np.zeros((0, max_nbr, 2), dtype=np.int64), np.zeros((0, max_nbr), bool)
-    tree = scipy.spatial.KDTree(pts)
-    _, knn = tree.query(pts, k=max_nbr + 1, distance_upper_bound=radius)
-    knn = knn[:, 1:]
+    if ties == "scipy":
+        tree = scipy.spatial.KDTree(pts)
+        _, knn = tree.query(pts, k=max_nbr + 1, distance_upper_bound=radius)
+        knn = knn[:, 1:]
+    else:
+        assert ties == "index", ties
+        knn = knn_by_index(pts, max_nbr, radius)
     src = np.tile(np.arange(n)[:, None], (1, max_nbr))
     valid = knn < n
     tgt = np.where(valid, knn, src)
@@ -385,47 +429,58 @@ def fuse_masks(tile_scores: Sequence[np.ndarray], tiles, H: int, W: int):
 
 
 def infer_one_img(sd: StateDict, spec: ModelSpec, img: np.ndarray, config, masks_override=None,
-                  return_edge_scores: bool = False) -> tuple:
+                  return_edge_scores: bool = False, tie_order: str = "numpy", knn_ties: str = "scipy",
+                  topo_fn=None) -> tuple:
     """Whole-scene driver (inferencer.py:61-234) on top of the oracle model.  `masks_override`
     (kp_mask, road_mask) lets a test continue from given fused masks; `return_edge_scores` also
-    returns {(src,tgt): mean score} before thresholding."""
+    returns {(src,tgt): mean score} before thresholding.  `tie_order` / `knn_ties` select how the two
+    third-party tie orders are resolved (see visiting_order / build_pair_queries); `topo_fn(batch_index,
+    feats, pts, prs, val) -> scores` replaces the oracle TopoNet (tests feed the CUDA scores through
+    the reference aggregation loop to check it bit for bit)."""
     from collections import defaultdict
     H = img.shape[0]
     bs = int(config["INFER_BATCH_SIZE"])
     tiles = get_patch_info_one_img(0, H, int(config["SAMPLE_MARGIN"]), int(config["PATCH_SIZE"]),
                                    int(config["INFER_PATCHES_PER_EDGE"]))
     scores_all, feats = [], []
+    dev0 = next(iter(sd.values())).device
+    skip_model = masks_override is not None and topo_fn is not None     # nothing of the oracle model is needed
     for b0 in range(0, len(tiles), bs):
         batch = tiles[b0:b0 + bs]
+        if skip_model:
+            feats.append(None)
+            continue
         rgb = torch.stack([torch.tensor(img[y0:y1, x0:x1, :], dtype=torch.float32)
                            for _, (x0, y0), (x1, y1) in batch], 0)
         with torch.no_grad():
-            sc, ft = infer_masks_and_img_features(sd, spec, rgb.to(next(iter(sd.values())).device))
+            sc, ft = infer_masks_and_img_features(sd, spec, rgb.to(dev0))
         feats.append(ft)
         scores_all.extend([s.cpu().numpy() for s in sc])
-    kp_mask, road_mask = fuse_masks(scores_all, tiles, img.shape[0], img.shape[1])
     if masks_override is not None:
         kp_mask, road_mask = masks_override
+    else:
+        kp_mask, road_mask = fuse_masks(scores_all, tiles, img.shape[0], img.shape[1])
     gp = extract_graph_points(kp_mask, road_mask, float(config["ITSC_THRESHOLD"]),
                               float(config["ROAD_THRESHOLD"]), float(config["ITSC_NMS_RADIUS"]),
-                              float(config["ROAD_NMS_RADIUS"]))
+                              float(config["ROAD_NMS_RADIUS"]), tie_order)
     if gp.shape[0] == 0:
         return gp, np.zeros((0, 2), dtype=np.int32), kp_mask, road_mask
     edge_sum, edge_cnt = defaultdict(float), defaultdict(float)
     K, R = int(config["MAX_NEIGHBOR_QUERIES"]), float(config["NEIGHBOR_RADIUS"])
     for bi, b0 in enumerate(range(0, len(tiles), bs)):
         batch = tiles[b0:b0 + bs]
-        q = [build_pair_queries(gp, t, K, R) for t in batch]
+        q = [build_pair_queries(gp, t, K, R, knn_ties) for t in batch]
         nmax = max(x[1].shape[0] for x in q)
         if nmax == 0:
             continue
         pad = lambda a: np.pad(a, [(0, nmax - a.shape[0])] + [(0, 0)] * (a.ndim - 1))
-        dev = feats[bi].device
+        dev = dev0
         pts = torch.tensor(np.stack([pad(x[1]) for x in q])).to(dev)
         prs = torch.tensor(np.stack([pad(x[2]) for x in q])).to(dev)
         val = torch.tensor(np.stack([pad(x[3]) for x in q])).to(dev)
         with torch.no_grad():
-            ts = infer_toponet(sd, spec, feats[bi], pts, prs, val)
+            ts = topo_fn(bi, feats[bi], pts, prs, val) if topo_fn is not None else \
+                infer_toponet(sd, spec, feats[bi], pts, prs, val)
         ts = torch.where(torch.isnan(ts), -100.0, ts).squeeze(-1).cpu().numpy()
         for ti in range(len(batch)):
             idx = q[ti][0]

@@ -12,7 +12,8 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libsamroad_b200.so"
 
-F32, I64, I32, U8 = 0, 1, 2, 3
+F32, I64, I32, U8, F64 = 0, 1, 2, 3, 4
+ABI_VERSION = 2
 TOPO_NORMAL, TOPO_NO_OFFSET, TOPO_NO_TRANSFORMER = 0, 1, 2
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 
@@ -31,7 +32,11 @@ class SamRoadCfg(C.Structure):
     ]
 
 
-_vp, _i, _f = C.c_void_p, C.c_int, C.c_float
+_vp, _i, _f, _d = C.c_void_p, C.c_int, C.c_float, C.c_double
+_ip = C.POINTER(C.c_int)
+
+# samroad_argsort_fn: int (*)(const void* keys, int key_dtype, int64_t n, int64_t* order_out, void* user)
+ARGSORT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int64, C.POINTER(C.c_int64), C.c_void_p)
 
 # name -> (restype, argtypes); mirrors include/samroad_b200.h one to one
 SIGNATURES = {
@@ -42,6 +47,14 @@ SIGNATURES = {
     "samroad_encode_masks": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "samroad_toponet": (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "samroad_fuse_masks": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "samroad_encode_masks_scene": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    "samroad_graph_create": (_i, [_i, C.POINTER(_vp)]),
+    "samroad_graph_destroy": (_i, [_vp]),
+    "samroad_extract_graph_points": (_i, [_vp, _vp, _vp, _i, _i, _d, _d, _d, _d, ARGSORT_FN, _vp, _vp, _i,
+                                          _ip, _vp, _vp]),
+    "samroad_pair_queries_plan": (_i, [_vp, _vp, _i, _vp, _i, _i, _d, _vp, _vp]),
+    "samroad_pair_queries_fill": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "samroad_aggregate_edges": (_i, [_vp, _vp, _vp, _i, _f, _vp, _i, _ip, _ip, _vp]),
     "samroad_encode_masks_host": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "samroad_infer_batch_host": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "samroad_timing_enable": (_i, [_vp, _i]),

@@ -18,7 +18,7 @@ CSRC = PKG_DIR / "csrc"
 OBJ_DIR = PKG_DIR / "_build"
 LIB_PATH = PKG_DIR / "libsamroad_b200.so"
 
-SOURCES = ["common.cu", "gemm_ops.cu", "kernels.cu", "attention.cu", "toponet.cu", "sam_decoder.cu", "model.cu"]
+SOURCES = ["common.cu", "gemm_ops.cu", "kernels.cu", "attention.cu", "toponet.cu", "sam_decoder.cu", "graph.cu", "model.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

@@ -256,13 +256,12 @@ static int launch_attention_tc(const __half* qkv, const float* qkv_bias, const _
   const int rows = rel_table_rows(WIN);
   if (int rc = make_tmap_f16_2d(&tmTab, tab, rows, 64, 64, rows)) return rc;
   auto kern = g_poly ? attention_tc_kernel<kWindow, WIN, true> : attention_tc_kernel<kWindow, WIN, false>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static uint64_t attr_devs = 0;          // one bit per CUDA device: function attributes are per device
+  if (first_use_on_device(&attr_devs)) {
     SRB_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<kWindow, WIN, false>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, AtcSmem<kWindow>::kBytes));
     SRB_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<kWindow, WIN, true>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, AtcSmem<kWindow>::kBytes));
-    attr_set = true;
   }
   AtcParams p;
   p.qkv_bias = qkv_bias; p.out = out; p.B = B; p.s = s; p.heads = heads; p.D = D;
@@ -301,10 +300,9 @@ static int launch_attention_tc80(const __half* qkv, const float* qkv_bias, const
   }
   if (int rc = make_tmap_f16_2d(&tmTab, tab, SM::NTAB, 128, 128, SM::NTAB)) return rc;
   auto kern = attention_tc80_kernel<kWindow, WIN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static uint64_t attr_devs = 0;          // one bit per CUDA device: function attributes are per device
+  if (first_use_on_device(&attr_devs)) {
     SRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
-    attr_set = true;
   }
   AtcParams p;
   p.qkv_bias = qkv_bias; p.out = out; p.B = B; p.s = s; p.heads = heads; p.D = D;
@@ -326,11 +324,15 @@ int encoder_attention(const __half* qkv, const float* qkv_bias, const float* rel
   if (B <= 0) return 0;
   // tensor-core path: head_dim 64; window 14 on any grid, global on 16x16 / 32x32 token grids
   const bool tc_ok = hd == 64 && !g_force_simt &&
-                     ((win == 14 && s >= 14) || (win == s && (s == 16 || s == 32)));
+                     ((win == 14 && s > 14) || (win == s && (s == 16 || s == 32)));
   if (tc_ok) {
     const __half* tab = rel_tab;
     if (!tab) {
-      static __half* scratch = nullptr;   // op-level calls without a pre-packed table
+      static __half* scratch_dev[64] = {nullptr};   // op-level calls without a pre-packed table (per device)
+      int dev = 0;
+      SRB_CUDA_OK(cudaGetDevice(&dev));
+      SRB_REQUIRE(dev >= 0 && dev < 64, "attention: device index %d", dev);
+      __half*& scratch = scratch_dev[dev];
       if (!scratch) SRB_CUDA_OK(cudaMalloc(&scratch, 128 * 64 * sizeof(__half)));
       SRB_TRY_RC(pack_rel_table(rel_h, rel_w, win, hd, scratch, st));
       tab = scratch;
@@ -341,11 +343,15 @@ int encoder_attention(const __half* qkv, const float* qkv_bias, const float* rel
   }
   // head_dim 80 (ViT-H): tensor-core kernel with two K-blocks per operand tile
   const bool tc80_ok = hd == 80 && !g_force_simt &&
-                       ((win == 14 && s >= 14) || (win == s && (s == 16 || s == 32)));
+                       ((win == 14 && s > 14) || (win == s && (s == 16 || s == 32)));
   if (tc80_ok) {
     const __half* tab = rel_tab;
     if (!tab) {
-      static __half* scratch80 = nullptr;
+      static __half* scratch80_dev[64] = {nullptr};
+      int dev = 0;
+      SRB_CUDA_OK(cudaGetDevice(&dev));
+      SRB_REQUIRE(dev >= 0 && dev < 64, "attention: device index %d", dev);
+      __half*& scratch80 = scratch80_dev[dev];
       if (!scratch80) SRB_CUDA_OK(cudaMalloc(&scratch80, 128 * 128 * sizeof(__half)));
       SRB_TRY_RC(pack_rel_table(rel_h, rel_w, win, hd, scratch80, st));
       tab = scratch80;

@@ -26,16 +26,25 @@ uint64_t launch_count(bool reset) {
 }
 
 int device_sm_count() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  static int cached[64] = {0};     // per device: a process may drive several GPUs
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
     int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
       return 148;
-    cached = n;
+    cached[dev] = n;
   }
-  return cached;
+  return cached[dev];
+}
+
+bool first_use_on_device(uint64_t* device_mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  const uint64_t bit = 1ull << dev;
+  if (*device_mask & bit) return false;
+  *device_mask |= bit;
+  return true;
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,

@@ -619,10 +619,9 @@ int launch_gemm_tc(const __half* A, int lda, const __half* W, int ldw, int M, in
   }
   if (int rc = make_tmap_f16_2d(&tmB, W, N, K, ldw, BN)) return rc;
   auto kern = gemm_tc_kernel<BN, STAGES, Epi>;
-  static bool attr_set = false;   // per template instantiation
-  if (!attr_set) {
+  static uint64_t attr_devs = 0;          // one bit per CUDA device: function attributes are per device   // per template instantiation
+  if (first_use_on_device(&attr_devs)) {
     SRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
-    attr_set = true;
   }
   const int num_tiles = ((M + kGemmBM - 1) / kGemmBM) * ((N + BN - 1) / BN);
   const int grid = num_tiles < device_sm_count() ? num_tiles : device_sm_count();

@@ -258,10 +258,9 @@ int launch_gemm_tc2(const __half* A, int lda, const __half* W, int ldw, int M, i
     if (int rc = make_tmap_f16_2d(&tmO, ep.out, M, N, ep.ldo, 32)) return rc;
   }
   auto kern = gemm_tc2_kernel<Epi>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static uint64_t attr_devs = 0;          // one bit per CUDA device: function attributes are per device
+  if (first_use_on_device(&attr_devs)) {
     SRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
-    attr_set = true;
   }
   const int num_tiles = ((M + 255) / 256) * (N / 256);
   const int max_clusters = device_sm_count() / 2;

@@ -266,10 +266,9 @@ int launch_gemm_tc2_resid(const __half* A, int lda, const __half* W, int ldw, in
     load_rows = 0;
   }
   auto kern = gemm_tc2_resid_kernel<STAGES, NB, kReduce>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static uint64_t attr_devs = 0;          // one bit per CUDA device: function attributes are per device
+  if (first_use_on_device(&attr_devs)) {
     SRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
-    attr_set = true;
   }
   const int num_tiles = ((M + 255) / 256) * (N / 256);
   const int max_clusters = device_sm_count() / 2;

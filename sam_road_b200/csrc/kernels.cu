@@ -140,6 +140,39 @@ int im2col_patch16(const void* rgb, int dtype, int B, int P, const float* mean,
 }
 
 // ------------------------------------------------------------------------------------------------
+// Tile crop (inferencer.py:43-58 crop_img_patch / get_batch_img_patches): uint8 scene [H,W,3] ->
+// uint8 tiles [B,P,P,3] at the given origins.  One thread = 4 destination bytes (one aligned store);
+// the source row starts at an arbitrary byte, so it is read bytewise (L1-resident, 3 B per pixel).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+crop_tiles_kernel(const uint8_t* __restrict__ scene, int W, const int* __restrict__ txy, int B, int P,
+                  uint8_t* __restrict__ out) {
+  const int row_words = P * 3 / 4;
+  const long total = static_cast<long>(B) * P * row_words;
+  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int wq = static_cast<int>(idx % row_words);
+  const int y = static_cast<int>((idx / row_words) % P);
+  const int b = static_cast<int>(idx / (static_cast<long>(row_words) * P));
+  const int x0 = __ldg(txy + 2 * b), y0 = __ldg(txy + 2 * b + 1);
+  const uint8_t* src = scene + (static_cast<size_t>(y0 + y) * W + x0) * 3 + wq * 4;
+  const uint32_t v = static_cast<uint32_t>(src[0]) | (static_cast<uint32_t>(src[1]) << 8) |
+                     (static_cast<uint32_t>(src[2]) << 16) | (static_cast<uint32_t>(src[3]) << 24);
+  reinterpret_cast<uint32_t*>(out)[idx] = v;
+}
+
+int crop_tiles(const uint8_t* scene, int H, int W, const int* tile_xy, int B, int P, uint8_t* out,
+               cudaStream_t st) {
+  SRB_REQUIRE(P % 4 == 0 && P > 0 && P <= H && P <= W, "crop_tiles: P=%d vs scene %dx%d", P, H, W);
+  if (B <= 0) return 0;
+  const long total = static_cast<long>(B) * P * (P * 3 / 4);
+  crop_tiles_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(scene, W, tile_xy, B, P, out);
+  SRB_CUDA_OK(cudaGetLastError());
+  note_launch();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // 3x3 / pad 1 im2col on NHWC fp16 (neck conv, image_encoder.py:96-102): one thread = 8 channels.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)

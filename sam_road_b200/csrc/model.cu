@@ -264,6 +264,7 @@ struct EncWs {
   __half* N1;      // [M, 256] neck conv1 + LN ; reused: D1 [M, 512] needs 2x -> own buffer below
   __half* FEAT;    // [M, 256] neck output (fp16 NHWC)
   __half* D1;      // [M, 512]
+  uint8_t* RGB;    // [B, P, P, 3] uint8 tiles cropped from a scene (samroad_encode_masks_scene)
   size_t total;
 };
 
@@ -286,6 +287,7 @@ EncWs layout_enc(const samroad_ctx* h, int B, void* base) {
   w.N1 = reinterpret_cast<__half*>(b + take(M * 256 * 2));
   w.FEAT = reinterpret_cast<__half*>(b + take(M * 256 * 2));
   w.D1 = reinterpret_cast<__half*>(b + take(M * 512 * 2));
+  w.RGB = reinterpret_cast<uint8_t*>(b + take(M * 768));      // B * P * P * 3 = M * 256 * 3
   w.total = off;
   return w;
 }
@@ -803,6 +805,24 @@ extern "C" int samroad_encode_masks(samroad_handle_t h, const void* rgb, int rgb
                          mask_scores, mask_logits, st));
   }
   return 0;
+}
+
+// Tiles addressed inside a uint8 scene that already lives on the device (inferencer.py:43-58,87-96
+// without the per-tile host crops and the synchronous float32 upload): crop on the device, then the
+// same path as samroad_encode_masks.
+extern "C" int samroad_encode_masks_scene(samroad_handle_t h, const uint8_t* scene, int H, int W,
+                                          const int32_t* tile_xy, int B, float* mask_scores,
+                                          float* mask_logits, float* image_embeddings, void* stream) {
+  SRB_TRY(check_handle(h, true));
+  SRB_REQUIRE(scene && tile_xy && image_embeddings, "samroad_encode_masks_scene: null argument");
+  if (B <= 0) return 0;
+  const int P = h->cfg.patch_size;
+  SRB_REQUIRE(H >= P && W >= P, "samroad_encode_masks_scene: scene %dx%d smaller than a %d tile", H, W, P);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SRB_TRY(ensure_bytes(&h->ws, &h->ws_bytes, layout_enc(h, B, nullptr).total));
+  EncWs w = layout_enc(h, B, h->ws);
+  SRB_T(KT_PATCH_IM2COL, 0, 2.0 * B * P * P * 3, crop_tiles(scene, H, W, tile_xy, B, P, w.RGB, st));
+  return samroad_encode_masks(h, w.RGB, SAMROAD_U8, B, mask_scores, mask_logits, image_embeddings, stream);
 }
 
 extern "C" int samroad_encode_masks_host(samroad_handle_t h, const void* rgb_host, int rgb_dtype,

@@ -22,6 +22,8 @@ enum Act : int {
 void set_last_error(const char* fmt, ...);
 const char* get_last_error();
 int device_sm_count();
+// true the first time it is called with this mask on the current CUDA device (then sets the bit)
+bool first_use_on_device(uint64_t* device_mask);
 void note_launch(int n = 1);
 uint64_t launch_count(bool reset);
 
@@ -49,6 +51,9 @@ int layernorm_f16(const float* x, const float* gamma, const float* beta, float e
 // rgb: [B,P,P,3] fp32 (dtype 0) or uint8 (dtype 1); out: [B*(P/16)^2, 768] fp16, k = ky*48+kx*3+c
 int im2col_patch16(const void* rgb, int dtype, int B, int P, const float* mean, const float* inv_std,
                    __half* out, cudaStream_t st);
+// scene: uint8 [H,W,3]; tile_xy: device int32 [B,2] origins (x0,y0) inside the scene; out: uint8 [B,P,P,3]
+int crop_tiles(const uint8_t* scene, int H, int W, const int* tile_xy, int B, int P, uint8_t* out,
+               cudaStream_t st);
 // x: [B*s*s, C] fp16 NHWC; out: [B*s*s, 9*C], k = (ky*3+kx)*C + c, zero padding 1
 int im2col_3x3(const __half* x, int B, int s, int C, __half* out, cudaStream_t st);
 int convert_f32_f16(const float* x, long n, __half* out, cudaStream_t st);

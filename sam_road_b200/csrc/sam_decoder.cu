@@ -471,11 +471,10 @@ int sam_decoder_forward(const SamDecoderWeights& W, const float* emb_nchw, int B
 
   const size_t layer_smem = (6 * kTok * kC + kTok * 2048 + 32 * 8 * 18) * sizeof(float);
   const size_t final_smem = (4 * kTok * kC + 32 * 8 * 18) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static uint64_t attr_devs = 0;          // one bit per CUDA device: function attributes are per device
+  if (first_use_on_device(&attr_devs)) {
     SRB_CUDA_OK(cudaFuncSetAttribute(sam_token_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(layer_smem)));
-    attr_set = true;
   }
   const int Mi = static_cast<int>(M);
 

@@ -82,8 +82,10 @@ topo_pair_kernel(const float* __restrict__ pst, const float* __restrict__ w_off,
                  float* __restrict__ x32, __half* __restrict__ x16) {
   const size_t tok = blockIdx.x;
   const int b = static_cast<int>(tok / tokens_per_b);
-  const long long src = load_index(pairs, pairs_dtype, tok * 2 + 0);
-  const long long tgt = load_index(pairs, pairs_dtype, tok * 2 + 1);
+  // indices are clamped into [0, N): an out-of-range pair (an IndexError in the reference) must not
+  // become an out-of-bounds read here
+  const long long src = min(max(load_index(pairs, pairs_dtype, tok * 2 + 0), 0LL), static_cast<long long>(N) - 1);
+  const long long tgt = min(max(load_index(pairs, pairs_dtype, tok * 2 + 1), 0LL), static_cast<long long>(N) - 1);
   const size_t ps = static_cast<size_t>(b) * N + src, pt = static_cast<size_t>(b) * N + tgt;
   float ox = 0.f, oy = 0.f;
   if (!zero_offset) {
@@ -252,11 +254,10 @@ int topo_transformer_fused(const TopoPairInputs& in, const __half* w_chunks, con
   SRB_REQUIRE(in.pairs_dtype == 1 || in.pairs_dtype == 2, "topo fused: pairs dtype %d", in.pairs_dtype);
   CUtensorMap tmW;
   if (int rc = make_tmap_f16_2d(&tmW, w_chunks, 18 * 128, 128, 128, 128)) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static uint64_t attr_devs = 0;          // one bit per CUDA device: function attributes are per device
+  if (first_use_on_device(&attr_devs)) {
     SRB_CUDA_OK(cudaFuncSetAttribute(toponet_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      kTtcSmemBytes));
-    attr_set = true;
   }
   TtcParams p;
   for (int l = 0; l < 3; ++l) {

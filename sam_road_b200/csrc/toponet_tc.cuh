@@ -260,8 +260,9 @@ toponet_tc_kernel(const __grid_constant__ CUtensorMap tmW, TtcParams p) {
       nx_ps = nx_pt = 0;
       if (t < p.num_tiles && tk < p.tokens) {
         const size_t b = static_cast<size_t>(tk) / p.tokens_per_b;
-        nx_ps = b * p.N + ttc_load_index(p.pairs, p.pairs_dtype, static_cast<size_t>(tk) * 2 + 0);
-        nx_pt = b * p.N + ttc_load_index(p.pairs, p.pairs_dtype, static_cast<size_t>(tk) * 2 + 1);
+        const long long nm1 = static_cast<long long>(p.N) - 1;    // clamp: no out-of-bounds gather on bad indices
+        nx_ps = b * p.N + min(max(ttc_load_index(p.pairs, p.pairs_dtype, static_cast<size_t>(tk) * 2 + 0), 0LL), nm1);
+        nx_pt = b * p.N + min(max(ttc_load_index(p.pairs, p.pairs_dtype, static_cast<size_t>(tk) * 2 + 1), 0LL), nm1);
         if (!p.zero_offset) {
           nx_ox = ttc_load_coord(p.points, p.pts_dtype, nx_pt * 2 + 0) -
                   ttc_load_coord(p.points, p.pts_dtype, nx_ps * 2 + 0);

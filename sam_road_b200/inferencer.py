@@ -3,39 +3,39 @@
     pred_nodes, pred_edges, keypoint_mask, road_mask = infer_one_img(net, img, config)
 
 Same signature, argument meaning and return values as the reference.  What changes is
-where the work happens:
-  * the uint8 scene is uploaded once; tiles are cropped on the device and fed to the encoder as uint8
-    (the reference converts every crop to float32 on the CPU and copies it synchronously,
-    inferencer.py:52-58,94);
+where the work happens -- everything between the uint8 scene going up and the graph coming down runs
+on the GPU:
+  * the uint8 scene is uploaded once; tiles are windows of it, cropped on the device and fed to the
+    encoder as uint8 (the reference converts every crop to float32 on the CPU and copies it
+    synchronously, inferencer.py:52-58,94);
   * mask fusion (inferencer.py:79-110) is one kernel that adds the tiles in tile-list order, so the
     uint8 masks are bit-identical to the reference's accumulation for identical scores;
+  * keypoint extraction (graph_extraction.py:130-139, graph_utils.py:572-591), the per-tile box query
+    + kNN pair construction (inferencer.py:126-197) and the edge aggregation (inferencer.py:206-230)
+    are device kernels behind `sam_road_b200.graph.SceneGraph` (csrc/graph.cu): exact greedy NMS in the
+    reference's visiting order, exact kNN, float32 sums in the reference's (tile, sample, pair) order;
   * with torch.distributed initialised, tiles are sharded over ranks in contiguous blocks, the
-    per-tile mask scores are exchanged with ONE all-gather (and the topology scores with another),
-    and every rank fuses in global tile order -> identical masks / graph on all ranks and at any
-    world size.
-Keypoint extraction and kNN pair construction stay on the CPU with the reference's semantics
-(graph_extraction.py:130-139, graph_utils.py:572-591, inferencer.py:126-197); the rtree box query is
-an inclusive numpy box test with ascending indices; the edge aggregation (inferencer.py:206-230) is
-vectorised but keeps the reference's float32 accumulation order.
+    per-tile mask scores are exchanged with ONE all-gather, the topology scores with one all-reduce of
+    a disjointly-written buffer, and every rank fuses / aggregates in global tile order -> identical
+    masks and graph on all ranks and at any world size.
+There is no CPU path: without the CUDA library every stage raises.
 """
 from __future__ import annotations
 
 import os
 import time
-from typing import List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
 
 from . import _lib
+from .graph import SceneGraph
 from .model import _cfg_get
 
 TileInfo = Tuple[int, Tuple[int, int], Tuple[int, int]]
 
 
-# --------------------------------------------------------------------------------------------------
-# host helpers (CPU, numpy)
-# --------------------------------------------------------------------------------------------------
 def get_patch_info_one_img(image_index: int, image_size: int, sample_margin: int, patch_size: int,
                            patches_per_edge: int) -> List[TileInfo]:
     """Tile grid: round(linspace(margin, size-(P+margin), n)), x outer / y inner (dataset.py:56-67)."""
@@ -44,93 +44,6 @@ def get_patch_info_one_img(image_index: int, image_size: int, sample_margin: int
     return [(image_index, (x, y), (x + patch_size, y + patch_size)) for x in origins for y in origins]
 
 
-def nms_points(points: np.ndarray, scores: np.ndarray, radius: float) -> np.ndarray:
-    """Greedy radius NMS in descending score order; scores > 1 are never suppressed
-    (graph_utils.py:572-591)."""
-    import scipy.spatial
-    order = np.argsort(scores)[::-1]
-    pts, sc = points[order, :], scores[order]
-    if pts.shape[0] == 0:
-        return pts
-    kept = np.ones(order.shape[0], dtype=bool)
-    tree = scipy.spatial.KDTree(pts)
-    for i in range(pts.shape[0]):
-        if not kept[i]:
-            continue
-        nbr = tree.query_ball_point(pts[i], r=radius)
-        kept[nbr] = sc[nbr] > 1.0
-        kept[i] = True
-    return pts[kept]
-
-
-def extract_graph_points(keypoint_mask: np.ndarray, road_mask: np.ndarray, config) -> np.ndarray:
-    """Threshold + 3x NMS, intersections prioritised (graph_extraction.py:24-28,130-139) -> [N,2] xy."""
-    def candidates(mask, thr):
-        sel = mask > thr
-        rc = np.column_stack(np.where(sel))
-        return rc[:, ::-1], mask[sel]
-    p0, s0 = candidates(keypoint_mask, _cfg_get(config, "ITSC_THRESHOLD") * 255)
-    k0 = nms_points(p0, s0, _cfg_get(config, "ITSC_NMS_RADIUS"))
-    p1, s1 = candidates(road_mask, _cfg_get(config, "ROAD_THRESHOLD") * 255)
-    k1 = nms_points(p1, s1, _cfg_get(config, "ROAD_NMS_RADIUS"))
-    pts = np.concatenate([k0, k1], axis=0)
-    pri = np.concatenate([np.ones(k0.shape[0]), np.zeros(k1.shape[0])], axis=0)
-    return nms_points(pts, pri, _cfg_get(config, "ROAD_NMS_RADIUS"))
-
-
-def build_pair_queries(graph_points: np.ndarray, tile: TileInfo, max_nbr: int, radius: float):
-    """Pair queries of one tile (inferencer.py:148-176): points inside the tile box (inclusive),
-    kNN (k+1, drop self) within `radius`, prefix-valid mask, invalid slots point back at the source."""
-    import scipy.spatial
-    _, (x0, y0), (x1, y1) = tile
-    gx, gy = graph_points[:, 0], graph_points[:, 1]
-    idx = np.nonzero((gx >= x0) & (gx <= x1) & (gy >= y0) & (gy <= y1))[0]
-    n = idx.shape[0]
-    pts = graph_points[idx, :] - np.array([[x0, y0]], dtype=graph_points.dtype)
-    if n == 0:
-        return idx, pts, np.zeros((0, max_nbr, 2), dtype=np.int64), np.zeros((0, max_nbr), dtype=bool)
-    _, knn = scipy.spatial.KDTree(pts).query(pts, k=max_nbr + 1, distance_upper_bound=radius)
-    knn = knn.reshape(n, -1)[:, 1:]
-    src = np.tile(np.arange(n)[:, None], (1, max_nbr))
-    valid = knn < n
-    tgt = np.where(valid, knn, src)
-    return idx, pts, np.stack([src, tgt], axis=-1), valid
-
-
-def aggregate_edges(all_pairs: Sequence[np.ndarray], all_valid: Sequence[np.ndarray],
-                    all_idx: Sequence[np.ndarray], all_scores: Sequence[np.ndarray],
-                    threshold: float) -> np.ndarray:
-    """Edge aggregation of inferencer.py:206-230, vectorised: per directed (src,tgt) the scores of all
-    valid slots are summed in float32 in (tile, sample, pair) order -- the reference's loop order and
-    NumPy-2 scalar arithmetic -- then averaged and thresholded; edges keep first-occurrence order."""
-    srcs, tgts, vals = [], [], []
-    for pairs, valid, idx, scores in zip(all_pairs, all_valid, all_idx, all_scores):
-        if pairs.shape[0] == 0:
-            continue
-        v = valid.reshape(-1)
-        p = pairs.reshape(-1, 2)[v]
-        srcs.append(idx[p[:, 0]])
-        tgts.append(idx[p[:, 1]])
-        vals.append(scores[: pairs.shape[0]].reshape(-1)[v].astype(np.float32))
-    if not srcs:
-        return np.zeros((0, 2), dtype=np.int64)
-    src, tgt, val = np.concatenate(srcs), np.concatenate(tgts), np.concatenate(vals)
-    val = np.where(np.isnan(val), np.float32(-100.0), val)        # inferencer.py:206
-    assert np.all((val >= 0.0) & (val <= 1.0)), "topology score outside [0,1]"   # inferencer.py:219
-    key = src.astype(np.int64) * (int(max(src.max(), tgt.max())) + 1) + tgt.astype(np.int64)
-    uniq, first, inv = np.unique(key, return_index=True, return_inverse=True)
-    sums = np.zeros(uniq.shape[0], dtype=np.float32)
-    np.add.at(sums, inv, val)                                      # sequential float32 adds, in order
-    counts = np.bincount(inv, minlength=uniq.shape[0]).astype(np.float32)
-    keep = (sums / counts) > np.float32(threshold)
-    order = np.argsort(first[keep], kind="stable")                 # dict insertion order
-    sel = np.nonzero(keep)[0][order]
-    return np.stack([src[first[sel]], tgt[first[sel]]], axis=1)
-
-
-# --------------------------------------------------------------------------------------------------
-# the driver
-# --------------------------------------------------------------------------------------------------
 def _shard(n_items: int, rank: int, world: int) -> Tuple[int, int, int]:
     """Contiguous block of items owned by `rank`; returns (begin, end, per_rank)."""
     per = (n_items + world - 1) // world
@@ -138,12 +51,23 @@ def _shard(n_items: int, rank: int, world: int) -> Tuple[int, int, int]:
     return b, min(n_items, b + per), per
 
 
+def batch_plan(n_tiles: int, batch_size: int, world: int) -> List[Tuple[int, int, int]]:
+    """Every rank's batches as (rank, first_tile, n) in global tile order.  All ranks compute the same
+    list, which fixes the layout of the exchanged topology-score buffer."""
+    out = []
+    for r in range(world):
+        lo, hi, _ = _shard(n_tiles, r, world)
+        for b0 in range(lo, hi, batch_size):
+            out.append((r, b0, min(batch_size, hi - b0)))
+    return out
+
+
 def fuse_masks_device(scores: torch.Tensor, tiles: Sequence[TileInfo], H: int, W: int):
     """scores [n_tiles,P,P,2] fp32 (device, tile-list order) -> uint8 keypoint / road masks [H,W]."""
     dev = scores.device
     P = scores.shape[1]
-    x0 = torch.tensor([t[1][0] for t in tiles], dtype=torch.int32, device=dev)
-    y0 = torch.tensor([t[1][1] for t in tiles], dtype=torch.int32, device=dev)
+    x0 = torch.tensor([t[1][0] for t in tiles], dtype=torch.int32).to(dev)
+    y0 = torch.tensor([t[1][1] for t in tiles], dtype=torch.int32).to(dev)
     kp = torch.empty((H, W), dtype=torch.uint8, device=dev)
     road = torch.empty((H, W), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
@@ -153,13 +77,36 @@ def fuse_masks_device(scores: torch.Tensor, tiles: Sequence[TileInfo], H: int, W
     return kp, road
 
 
+_GRAPHS: Dict[int, SceneGraph] = {}
+_PINNED: Dict[Tuple[int, int], Tuple[torch.Tensor, torch.Tensor]] = {}
+
+
+def _pinned_masks(H: int, W: int):
+    """Page-locked staging for the two uint8 masks (allocated once per scene size; the caller gets copies)."""
+    if (H, W) not in _PINNED:
+        _PINNED.clear()
+        _PINNED[(H, W)] = (torch.empty((H, W), dtype=torch.uint8).pin_memory(),
+                           torch.empty((H, W), dtype=torch.uint8).pin_memory())
+    return _PINNED[(H, W)]
+
+
+def _scene_graph(device: torch.device) -> SceneGraph:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _GRAPHS:
+        _GRAPHS[idx] = SceneGraph(torch.device("cuda", idx))
+    return _GRAPHS[idx]
+
+
 def infer_one_img(net, img: np.ndarray, config, device: Optional[torch.device] = None,
-                  group=None, timings: Optional[dict] = None, shard: bool = True):
+                  group=None, timings: Optional[dict] = None, shard: bool = True,
+                  nms_tie_order: Optional[str] = None):
     """Whole-scene inference (inferencer.py:61-234).
 
-    img: uint8 [H,W,3] RGB.  Returns (pred_nodes [N,2] (r,c), pred_edges [E,2], fused_keypoint_mask
-    uint8 [H,W], fused_road_mask uint8 [H,W]) -- identical on every rank when run distributed.
-    `shard=False` makes a rank process the whole scene alone even if torch.distributed is up."""
+    img: uint8 [H,W,3] RGB.  Returns (pred_nodes int64 [N,2] (r,c), pred_edges int64 [E,2],
+    fused_keypoint_mask uint8 [H,W], fused_road_mask uint8 [H,W]) -- identical on every rank when run
+    distributed.  `shard=False` makes a rank process the whole scene alone even if torch.distributed
+    is up.  `nms_tie_order`: "numpy" (default; this host's np.argsort decides ties like the reference)
+    or "stable" (device-only sort), see sam_road_b200.graph."""
     import torch.distributed as dist
     distributed = shard and dist.is_available() and dist.is_initialized()
     rank = dist.get_rank(group) if distributed else 0
@@ -167,72 +114,110 @@ def infer_one_img(net, img: np.ndarray, config, device: Optional[torch.device] =
     if device is None:
         device = next(net.parameters()).device
     device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError(f"sam_road_b200.infer_one_img runs on CUDA only, got '{device}'")
     t_start = time.perf_counter()
 
     H, W = int(img.shape[0]), int(img.shape[1])
     P = int(_cfg_get(config, "PATCH_SIZE"))
+    s = P // 16
     bs = int(_cfg_get(config, "INFER_BATCH_SIZE"))
     tiles = get_patch_info_one_img(0, H, int(_cfg_get(config, "SAMPLE_MARGIN")), P,
                                    int(_cfg_get(config, "INFER_PATCHES_PER_EDGE")))
     n_tiles = len(tiles)
+    tile_xy = np.array([t[1] for t in tiles], dtype=np.int32).reshape(-1, 2)
     lo, hi, per = _shard(n_tiles, rank, world)
-    my_tiles = tiles[lo:hi]
+    n_mine = hi - lo
 
     # ---- pass 1: masks + image features of the tiles this rank owns -------------------------------
-    img_d = torch.as_tensor(np.ascontiguousarray(img), device=device)           # one H2D of the scene
-    scores_all = torch.zeros((per * world, P, P, 2), dtype=torch.float32, device=device)
+    img_d = torch.as_tensor(np.ascontiguousarray(img)).to(device)               # one H2D of the scene
+    scores_all = torch.empty((per * world, P, P, 2), dtype=torch.float32, device=device)
     my_scores = scores_all[rank * per: rank * per + per]
-    feats: List[torch.Tensor] = []
-    for b0 in range(0, len(my_tiles), bs):
-        batch = my_tiles[b0:b0 + bs]
-        rgb = torch.stack([img_d[y0:y1, x0:x1, :] for _, (x0, y0), (x1, y1) in batch], 0)
-        sc, ft = net.infer_masks_and_img_features(rgb)
-        my_scores[b0:b0 + len(batch)].copy_(sc)
-        feats.append(ft)
+    feats = torch.empty((max(n_mine, 1), 256, s, s), dtype=torch.float32, device=device)
+    scene_call = getattr(net, "infer_masks_and_img_features_scene", None)
+    for b0 in range(0, n_mine, bs):
+        nb = min(bs, n_mine - b0)
+        if scene_call is not None:
+            scene_call(img_d, tile_xy[lo + b0: lo + b0 + nb], out_scores=my_scores[b0:b0 + nb],
+                       out_emb=feats[b0:b0 + nb])
+        else:    # any object with the reference's model interface
+            rgb = torch.stack([img_d[y0:y1, x0:x1, :] for _, (x0, y0), (x1, y1) in tiles[lo + b0: lo + b0 + nb]], 0)
+            sc, ft = net.infer_masks_and_img_features(rgb)
+            my_scores[b0:b0 + nb].copy_(sc)
+            feats[b0:b0 + nb].copy_(ft)
     if world > 1:   # the exchange step: one all-gather of per-tile mask scores
+        if n_mine < per:
+            my_scores[n_mine:].zero_()
         dist.all_gather_into_tensor(scores_all, my_scores.clone(), group=group)
     kp_d, road_d = fuse_masks_device(scores_all[:n_tiles], tiles, H, W)
-    kp_mask, road_mask = kp_d.cpu().numpy(), road_d.cpu().numpy()
+    # the masks are return values: start their download now, it overlaps the graph stage
+    kp_h, road_h = _pinned_masks(H, W)
+    kp_h.copy_(kp_d, non_blocking=True)
+    road_h.copy_(road_d, non_blocking=True)
+    masks_done = torch.cuda.Event()
+    masks_done.record()
+    if timings is not None:
+        torch.cuda.synchronize(device)
     t_pass1 = time.perf_counter()
 
-    # ---- keypoints (CPU, every rank: deterministic) -------------------------------------------------
-    graph_points = extract_graph_points(kp_mask, road_mask, config)
-    if graph_points.shape[0] == 0:
-        return graph_points, np.zeros((0, 2), dtype=np.int32), kp_mask, road_mask
+    # ---- keypoints (device) ------------------------------------------------------------------------------
+    gx = _scene_graph(device)
+    points_d = gx.extract_graph_points(kp_d, road_d, _cfg_get(config, "ITSC_THRESHOLD"),
+                                       _cfg_get(config, "ROAD_THRESHOLD"),
+                                       _cfg_get(config, "ITSC_NMS_RADIUS"),
+                                       _cfg_get(config, "ROAD_NMS_RADIUS"), tie_order=nms_tie_order)
+    n_points = int(points_d.shape[0])
     t_points = time.perf_counter()
+    if n_points == 0:    # inferencer.py:123-124
+        masks_done.synchronize()
+        if timings is not None:
+            timings.update(pass1_s=t_pass1 - t_start, keypoints_s=t_points - t_pass1, pass2_s=0.0,
+                           total_s=time.perf_counter() - t_start, n_tiles=n_tiles, n_points=0,
+                           graph_stats=dict(gx.stats))
+        return (np.zeros((0, 2), dtype=np.int64), np.zeros((0, 2), dtype=np.int32), kp_h.numpy().copy(),
+                road_h.numpy().copy())
 
-    # ---- pass 2: TopoNet on the stored features ---------------------------------------------------------
+    # ---- pass 2: TopoNet on the stored features -------------------------------------------------------
     K = int(_cfg_get(config, "MAX_NEIGHBOR_QUERIES"))
     R = float(_cfg_get(config, "NEIGHBOR_RADIUS"))
-    queries = [build_pair_queries(graph_points, t, K, R) for t in tiles]   # cheap, needed by rank 0
-    nmax = max((q[1].shape[0] for q in queries), default=0)
-    topo_all = torch.zeros((per * world, max(nmax, 1), K), dtype=torch.float32, device=device)
-    my_topo = topo_all[rank * per: rank * per + per]
-    if nmax > 0:
-        def pad(a):
-            return np.pad(a, [(0, nmax - a.shape[0])] + [(0, 0)] * (a.ndim - 1))
-        for bi, b0 in enumerate(range(0, len(my_tiles), bs)):
-            q = queries[lo + b0: min(lo + b0 + bs, hi)]     # this rank's tiles of the batch only
-            if max(x[1].shape[0] for x in q) == 0:       # inferencer.py:188-189
-                continue
-            pts = torch.as_tensor(np.stack([pad(x[1]) for x in q]), device=device)
-            prs = torch.as_tensor(np.stack([pad(x[2]) for x in q]), device=device)
-            val = torch.as_tensor(np.stack([pad(x[3]) for x in q]), device=device)
-            ts = net.infer_toponet(feats[bi], pts, prs, val)
-            my_topo[b0:b0 + len(q)].copy_(ts.squeeze(-1))
-    if world > 1:
-        dist.all_gather_into_tensor(topo_all, my_topo.clone(), group=group)
-    topo_np = topo_all[:n_tiles].cpu().numpy()
-    pred_edges = aggregate_edges([q[2] for q in queries], [q[3] for q in queries],
-                                 [q[0] for q in queries], list(topo_np),
-                                 float(_cfg_get(config, "TOPO_THRESHOLD")))
+    counts = gx.plan_pair_queries(points_d, tile_xy, P, R)
+    # layout of the scene-wide score buffer: per batch [n, nmax_of_the_batch, K] (inferencer.py:179-185
+    # pads every batch to its own maximum); batches with no point at all are skipped (188-189)
+    plan = batch_plan(n_tiles, bs, world)
+    tile_off = np.full(n_tiles, -1, dtype=np.int64)
+    batch_nmax, cursor = [], 0
+    for (_, b0, nb) in plan:
+        nmax = int(counts[b0:b0 + nb].max()) if nb > 0 else 0
+        batch_nmax.append(nmax)
+        if nmax > 0:
+            tile_off[b0:b0 + nb] = cursor + np.arange(nb, dtype=np.int64) * (nmax * K)
+            cursor += nb * nmax * K
+    topo_flat = torch.zeros((max(cursor, 1),), dtype=torch.float32, device=device)
+    for (r, b0, nb), nmax in zip(plan, batch_nmax):
+        if r != rank or nmax == 0:
+            continue
+        pts, prs, val = gx.fill_batch(b0, nb, nmax, K)
+        out = topo_flat[int(tile_off[b0]): int(tile_off[b0]) + nb * nmax * K]
+        if scene_call is not None:
+            net.infer_toponet(feats[b0 - lo: b0 - lo + nb], pts, prs, val, out=out)
+        else:
+            out.copy_(net.infer_toponet(feats[b0 - lo: b0 - lo + nb], pts, prs, val).reshape(-1))
+    if world > 1:   # every element is written by exactly one rank (zeros elsewhere): the sum is exact
+        dist.all_reduce(topo_flat, op=dist.ReduceOp.SUM, group=group)
+    edges_d = gx.aggregate_edges(topo_flat, tile_off, K, float(_cfg_get(config, "TOPO_THRESHOLD")))
+    graph_points = points_d.cpu().numpy()
+    pred_edges = edges_d.cpu().numpy()
+    if pred_edges.shape[0] == 0:
+        pred_edges = np.array([]).reshape(-1, 2)          # what np.array([]).reshape(-1, 2) gives the reference
     pred_nodes = graph_points[:, ::-1]   # to (r, c), inferencer.py:230
+    masks_done.synchronize()
     if timings is not None:
         t_end = time.perf_counter()
         timings.update(pass1_s=t_pass1 - t_start, keypoints_s=t_points - t_pass1,
                        pass2_s=t_end - t_points, total_s=t_end - t_start, n_tiles=n_tiles,
-                       n_points=int(graph_points.shape[0]))
-    return pred_nodes, pred_edges, kp_mask, road_mask
+                       n_points=n_points, n_edges=int(pred_edges.shape[0]), graph_stats=dict(gx.stats),
+                       topo_samples=int(sum(nb * nm for (_, _, nb), nm in zip(plan, batch_nmax))))
+    return pred_nodes, pred_edges, kp_h.numpy().copy(), road_h.numpy().copy()
 
 
 # --------------------------------------------------------------------------------------------------

@@ -292,10 +292,30 @@ class SAMRoad(_Base):
     def __del__(self):
         try:
             lib = _lib.load()
-            for h in self._handles.values():
+            for h in self.__dict__.get("_handles", {}).values():
                 lib.samroad_destroy(h)
         except Exception:
             pass
+
+    # C handles are owned by exactly one Python object: copies / unpickled objects create their own
+    # on first use (copy.deepcopy of a module would otherwise destroy the same handle twice).
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["_handles"] = {}
+        state["_synced_version"] = {}
+        return state
+
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k in ("_handles", "_synced_version"):
+                new.__dict__[k] = {}
+            else:
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
 
     # ---- inference entry points ----------------------------------------------------------------------
     @staticmethod
@@ -304,17 +324,28 @@ class SAMRoad(_Base):
             return rgb.contiguous(), _lib.U8
         return rgb.to(torch.float32).contiguous(), _lib.F32
 
-    def _encode(self, rgb: torch.Tensor, want_logits: bool):
+    def _out_buffers(self, B, device, want_logits, out_scores, out_emb):
+        P, s = self.image_size, self.image_size // 16
+        if out_scores is None:
+            out_scores = torch.empty((B, P, P, 2), dtype=torch.float32, device=device)
+        if out_emb is None:
+            out_emb = torch.empty((B, 256, s, s), dtype=torch.float32, device=device)
+        for t, shape in ((out_scores, (B, P, P, 2)), (out_emb, (B, 256, s, s))):
+            if tuple(t.shape) != shape or t.dtype != torch.float32 or not t.is_contiguous() or \
+                    t.device != device:
+                raise ValueError(f"output buffer must be contiguous float32 {shape} on {device}")
+        logits = torch.empty_like(out_scores) if want_logits else None
+        return out_scores, logits, out_emb
+
+    def _encode(self, rgb: torch.Tensor, want_logits: bool, out_scores=None, out_emb=None):
         if rgb.dim() != 4 or rgb.shape[-1] != 3 or rgb.shape[1] != self.image_size or \
                 rgb.shape[2] != self.image_size:
             raise ValueError(f"rgb must be [B,{self.image_size},{self.image_size},3], got "
                              f"{tuple(rgb.shape)}")
         h = self._handle(rgb.device)
-        B, P, s = rgb.shape[0], self.image_size, self.image_size // 16
+        B = rgb.shape[0]
         x, dt = self._prep_rgb(rgb)
-        scores = torch.empty((B, P, P, 2), dtype=torch.float32, device=rgb.device)
-        logits = torch.empty_like(scores) if want_logits else None
-        emb = torch.empty((B, 256, s, s), dtype=torch.float32, device=rgb.device)
+        scores, logits, emb = self._out_buffers(B, rgb.device, want_logits, out_scores, out_emb)
         if B > 0:
             with torch.cuda.device(rgb.device):
                 _lib.check(_lib.load().samroad_encode_masks(
@@ -322,11 +353,50 @@ class SAMRoad(_Base):
                     _lib.current_stream_ptr()), "samroad_encode_masks")
         return scores, logits, emb
 
-    def _topo(self, image_embeddings, graph_points, pairs, valid, want_logits: bool):
+    @torch.no_grad()
+    def infer_masks_and_img_features_scene(self, scene_u8: torch.Tensor, tile_xy: torch.Tensor,
+                                           out_scores=None, out_emb=None):
+        """`infer_masks_and_img_features` for tiles that are windows of a uint8 scene [H,W,3] already
+        on the device: tile_xy = host int [B,2] origins (x0,y0).  Replaces the host crops and the float32
+        upload of inferencer.py:43-58,87-96; results equal those of the cropped-tile call bit for bit."""
+        if scene_u8.dtype != torch.uint8 or scene_u8.dim() != 3 or scene_u8.shape[-1] != 3 or \
+                not scene_u8.is_contiguous():
+            raise ValueError("scene must be a contiguous uint8 [H,W,3] tensor")
+        dev = scene_u8.device
+        h = self._handle(dev)
+        xy_host = torch.as_tensor(tile_xy).to(device="cpu", dtype=torch.int32).reshape(-1, 2).contiguous()
+        B = xy_host.shape[0]
+        H, W = int(scene_u8.shape[0]), int(scene_u8.shape[1])
+        P = self.image_size
+        if B > 0:    # validated on the host (origins come from the host tile list): no device sync
+            lo, hi = xy_host.min(dim=0).values.tolist(), xy_host.max(dim=0).values.tolist()
+            if lo[0] < 0 or lo[1] < 0 or hi[0] + P > W or hi[1] + P > H:
+                raise ValueError("tile origin outside the scene")
+        xy = xy_host.to(dev, non_blocking=True)
+        scores, _, emb = self._out_buffers(B, dev, False, out_scores, out_emb)
+        if B > 0:
+            with torch.cuda.device(dev):
+                _lib.check(_lib.load().samroad_encode_masks_scene(
+                    h, scene_u8.data_ptr(), H, W, xy.data_ptr(), B, scores.data_ptr(), None,
+                    emb.data_ptr(), _lib.current_stream_ptr()), "samroad_encode_masks_scene")
+        return scores, emb
+
+    def _topo(self, image_embeddings, graph_points, pairs, valid, want_logits: bool, out_scores=None):
         dev = image_embeddings.device
         h = self._handle(dev)
+        if pairs.dim() != 4 or pairs.shape[-1] != 2 or graph_points.dim() != 3 or \
+                graph_points.shape[-1] != 2 or tuple(valid.shape) != tuple(pairs.shape[:3]):
+            raise ValueError("expected graph_points [B,N,2], pairs [B,Ns,Np,2], valid [B,Ns,Np]; got "
+                             f"{tuple(graph_points.shape)}, {tuple(pairs.shape)}, {tuple(valid.shape)}")
         B, Ns, Np = pairs.shape[0], pairs.shape[1], pairs.shape[2]
         N = graph_points.shape[1]
+        s = self.image_size // 16
+        if tuple(image_embeddings.shape) != (B, 256, s, s) or graph_points.shape[0] != B:
+            raise ValueError(f"image_embeddings must be [{B},256,{s},{s}] and graph_points [{B},N,2]; got "
+                             f"{tuple(image_embeddings.shape)}, {tuple(graph_points.shape)}")
+        for name, t in (("graph_points", graph_points), ("pairs", pairs), ("valid", valid)):
+            if t.device != dev:     # the reference raises a device-mismatch error here as well
+                raise RuntimeError(f"{name} is on {t.device} but image_embeddings is on {dev}")
         emb = image_embeddings.to(torch.float32).contiguous()
         if graph_points.dtype == torch.int64:
             pts, pdt = graph_points.contiguous(), _lib.I64
@@ -338,15 +408,24 @@ class SAMRoad(_Base):
             prs, qdt = pairs.contiguous(), _lib.I32
         else:
             prs, qdt = pairs.to(torch.int64).contiguous(), _lib.I64
-        val = valid.to(torch.bool).contiguous().view(torch.uint8)
-        scores = torch.empty((B, Ns, Np, 1), dtype=torch.float32, device=dev)
-        logits = torch.empty_like(scores) if want_logits else None
+        val = valid.contiguous() if valid.dtype == torch.uint8 else \
+            valid.to(torch.bool).contiguous().view(torch.uint8)
+        if out_scores is None:
+            scores = torch.empty((B, Ns, Np, 1), dtype=torch.float32, device=dev)
+        else:
+            scores = out_scores
+            if scores.numel() != B * Ns * Np or scores.dtype != torch.float32 or \
+                    not scores.is_contiguous() or scores.device != dev:
+                raise ValueError("out_scores must be a contiguous float32 buffer of B*Ns*Np elements")
+        logits = torch.empty((B, Ns, Np, 1), dtype=torch.float32, device=dev) if want_logits else None
         if B * Ns * Np > 0:
+            # emb / pts / prs / val stay referenced until the call returns (stream-ordered kernels
+            # launched by it read them; the caching allocator reuses freed blocks only stream-ordered)
             with torch.cuda.device(dev):
                 _lib.check(_lib.load().samroad_toponet(
-                    h, emb.data_ptr(), pts.to(dev).data_ptr(), pdt, prs.to(dev).data_ptr(), qdt,
-                    val.to(dev).data_ptr(), B, N, Ns, Np, _lib.ptr(logits), scores.data_ptr(),
-                    _lib.current_stream_ptr()), "samroad_toponet")
+                    h, emb.data_ptr(), pts.data_ptr(), pdt, prs.data_ptr(), qdt, val.data_ptr(), B, N,
+                    Ns, Np, _lib.ptr(logits), scores.data_ptr(), _lib.current_stream_ptr()),
+                    "samroad_toponet")
         return logits, scores
 
     @torch.no_grad()
@@ -364,9 +443,10 @@ class SAMRoad(_Base):
         return scores, emb
 
     @torch.no_grad()
-    def infer_toponet(self, image_embeddings, graph_points, pairs, valid):
-        """topo_scores[B,Ns,Np,1] -- model.py:498-508."""
-        return self._topo(image_embeddings, graph_points, pairs, valid, False)[1]
+    def infer_toponet(self, image_embeddings, graph_points, pairs, valid, out=None):
+        """topo_scores[B,Ns,Np,1] -- model.py:498-508.  `out` (extension): a contiguous float32 buffer
+        of B*Ns*Np elements the scores are written into."""
+        return self._topo(image_embeddings, graph_points, pairs, valid, False, out_scores=out)[1]
 
     def training_step(self, *a, **k):
         raise NotImplementedError("sam_road_b200.SAMRoad is inference-only (SURVEY.md §8b)")

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in include/samroad_b200.h but not exported"
     assert set(_lib.SIGNATURES) == set(names), set(_lib.SIGNATURES) ^ set(names)
     bound = _lib.load()
-    assert bound.samroad_abi_version() == 1
+    assert bound.samroad_abi_version() == 2
 
 
 def test_cfg_struct_matches_header():

@@ -64,6 +64,8 @@ def _maxabs(a, b):
     ("vith_256", 256, "vit_h", 1, 0),
     ("vitb_256_samdec", 256, "vit_b", 3, 0),       # USE_SAM_DECODER: True (archived configs)
     ("vitb_512_samdec", 512, "vit_b", 2, 0),
+    ("vitl_256", 256, "vit_l", 2, 0),              # config/toponet_vitl_256.yaml
+    ("vitb_1024", 1024, "vit_b", 1, 0),            # config/toponet_vitb_1024.yaml (64x64 token grid)
 ])
 def test_encode_and_topo_parity(name, patch, version, B, lora):
     cfg = _config(patch, version, lora=lora, samdec=name.endswith("samdec"))
@@ -110,6 +112,60 @@ def test_encode_and_topo_parity(name, patch, version, B, lora):
     assert rep["topo_logit_maxabs_valid"] <= TOL_LOGIT, rep
     assert rep["topo_logit_maxabs_all"] <= 3 * TOL_LOGIT, rep
     assert rep["mask_score_maxabs"] <= TOL_LOGIT and rep["topo_score_maxabs_valid"] <= TOL_LOGIT
+
+
+def test_benched_configuration_b64_composition():
+    """The configuration bench.py times: ViT-B @512, B = 64 tiles in ONE call -- 2-CTA GEMMs, TMA
+    reduce-add shortcut epilogues, snake traversal, persistent attention CTAs running dozens of units.
+    (a) 4 of the 64 tiles against the oracle at the 1e-3 tolerance; (b) the same 4 tiles from a B = 4
+    call with every GEMM on the 1-CTA kernels and ascending traversal (debug mode 1|16): the B = 64
+    result may differ from it only by the rounding of the shortcut add (TMA reduce-add adds (acc + b) to
+    x in L2, the register path adds in another association); (c) with the shortcut streamed through smem
+    instead (mode 4: bit-identical arithmetic to the register path) B = 64 must equal B = 4 bit for bit."""
+    from sam_road_b200 import _lib
+    lib = _lib.load()
+    cfg = _config(512)
+    spec, sd, net = _build(cfg, seed=0)
+    B = 64
+    rgb = synth.make_tiles(B, 512, seed=21).to(DEV)
+    pts, prs, val = [t.to(DEV) for t in synth.make_topo_inputs(B, 512, 256, seed=22, ragged=False)]
+    sel = [0, 21, 42, 63]
+    try:
+        lib.samroad_debug_disable_2cta_gemm(0)
+        logits64, scores64, tl64, ts64 = net(rgb, pts, prs, val)
+        _, feat64 = net.infer_masks_and_img_features(rgb)
+        lib.samroad_debug_disable_2cta_gemm(4)
+        logits64s, _, tl64s, _ = net(rgb, pts, prs, val)
+        _, feat64s = net.infer_masks_and_img_features(rgb)
+        lib.samroad_debug_disable_2cta_gemm(1 | 16)
+        logits4, scores4, tl4, ts4 = net(rgb[sel], pts[sel], prs[sel], val[sel])
+        _, feat4 = net.infer_masks_and_img_features(rgb[sel])
+    finally:
+        lib.samroad_debug_disable_2cta_gemm(0)
+    with torch.no_grad():
+        o = O.forward(sd, spec, rgb[sel].float(), pts[sel], prs[sel], val[sel])
+    v = val[sel].unsqueeze(-1)
+    rep = {
+        "mask_logit_maxabs_b64_vs_oracle": _maxabs(logits64[sel], o[0]),
+        "topo_logit_maxabs_valid_b64_vs_oracle": ((tl64[sel] - o[2]).abs() * v).max().item(),
+        "mask_logit_maxabs_b4_1cta_vs_oracle": _maxabs(logits4, o[0]),
+        "mask_logit_maxabs_b64_vs_b4": _maxabs(logits64[sel], logits4),
+        "feat_maxabs_b64_vs_b4": _maxabs(feat64[sel], feat4),
+        "smem_shortcut_variant_bit_equal": bool(torch.equal(logits64s[sel], logits4) and
+                                                torch.equal(feat64s[sel], feat4) and torch.equal(tl64s[sel], tl4)),
+    }
+    _REPORT["vitb_512_b64_composition"] = rep
+    print(json.dumps(rep))
+    assert torch.isfinite(logits64).all() and torch.isfinite(tl64).all()
+    assert rep["mask_logit_maxabs_b64_vs_oracle"] <= TOL_LOGIT, rep
+    assert rep["topo_logit_maxabs_valid_b64_vs_oracle"] <= TOL_LOGIT, rep
+    assert rep["mask_logit_maxabs_b4_1cta_vs_oracle"] <= TOL_LOGIT, rep
+    assert rep["smem_shortcut_variant_bit_equal"], rep
+    assert rep["mask_logit_maxabs_b64_vs_b4"] <= 1e-4 and rep["feat_maxabs_b64_vs_b4"] <= 1e-3, rep
+    # every tile of the batch is computed independently of its neighbours: permuting the batch permutes the output
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(0)).to(DEV)
+    logits_p = net(rgb[perm], pts[perm], prs[perm], val[perm])[0]
+    assert torch.equal(logits_p, logits64[perm])
 
 
 def test_parity_with_wide_logits():

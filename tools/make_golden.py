@@ -151,11 +151,17 @@ def main():
     assert ref_loader.available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if "--only-new" in sys.argv:      # fixtures added in round 2 (the round-1 files stay byte-identical)
+        model_fixture("vitl_256", _cfg(256, version="vit_l"), seed=6, n_points=16)
+        model_fixture("vitb_1024", _cfg(1024), seed=7, n_points=40)
+        return
     model_fixture("vitb_256", _cfg(256), seed=0, n_points=24)
     model_fixture("vitb_512", _cfg(512), seed=1, n_points=40)
     model_fixture("vitb_256_lora4", _cfg(256, lora=4), seed=2, n_points=16)
     model_fixture("vitb_256_samdec", _cfg(256, samdec=True), seed=3, n_points=16)
     model_fixture("vith_256", _cfg(256, version="vit_h"), seed=4, n_points=16)
+    model_fixture("vitl_256", _cfg(256, version="vit_l"), seed=6, n_points=16)
+    model_fixture("vitb_1024", _cfg(1024), seed=7, n_points=40)
     toponet_fixture()
     tileloop_fixture()
 
