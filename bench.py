@@ -1,19 +1,23 @@
 #!/usr/bin/env python
 """Benchmark of the sam_road tiled-inference hot path on B200 (contract: see the task brief / DESIGN.md).
 
-    python bench.py --gpus 1 --steps 5 --warmup 3                 # this framework (CUDA, sm_100a)
+    python bench.py --gpus 1 --steps 20 --warmup 3                # this framework (CUDA, sm_100a)
+    python bench.py --workload c4                                 # another BASELINE configuration
     python bench.py --impl reference --steps 3 --warmup 1         # reference algorithm on host CPU cores
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1], `toponet_vitb_512_cityscale`): one "step" is one pass of the hot
-path over one INFER_BATCH_SIZE=64 batch of synthetic 512x512 RGB tiles per GPU: ViT-B encoder + naive
+Default workload (BASELINE.json configs[1], `toponet_vitb_512_cityscale`): one "step" is one pass of the
+hot path over one INFER_BATCH_SIZE=64 batch of synthetic 512x512 RGB tiles per GPU: ViT-B encoder + naive
 mask decoder + TopoNet on 256 keypoints x 16 neighbour pairs per tile.  Weights are seeded random
 tensors with the reference's state_dict layout; data is synthetic (no network for datasets/ckpts).
 
 Printed JSON (one line, rank 0):
-  value     tiles/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
-  e2e       same metric through the host-buffer C-ABI call (pinned host tiles in, results out)
-  roofline  dominant kernel class: algorithmic FLOPs / CUDA-event duration vs MEASURED_PEAKS.json
+  value      tiles/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e        same metric through the host-buffer C-ABI call (pinned host tiles in, results out), the two
+             staging slots alternating so that a batch's downloads overlap the next batch's upload + compute
+  e2e_scene  whole scenes through the drop-in `infer_one_img` (uint8 scene in host memory -> nodes, edges
+             and the two uint8 masks in host memory): tiles/s = tiles of the scene / wall time
+  roofline   dominant kernel class: algorithmic FLOPs / CUDA-event duration vs MEASURED_PEAKS.json
   cpu_baseline  the CPU oracle (port of the reference algorithm) timed on this box's host cores
 """
 from __future__ import annotations
@@ -31,15 +35,43 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-WORKLOAD = "toponet_vitb_512_cityscale"
-CONFIG = dict(SAM_VERSION="vit_b", PATCH_SIZE=512, USE_SAM_DECODER=False, ENCODER_LORA=False,
-              TOPONET_VERSION="normal", NO_SAM=False, INFER_BATCH_SIZE=64)
-POINTS_PER_TILE = 256
-METRIC = "512x512 ViT-B tiles/sec"
+_BASE = dict(USE_SAM_DECODER=False, ENCODER_LORA=False, TOPONET_VERSION="normal", NO_SAM=False,
+             INFER_BATCH_SIZE=64)
+TOPO_FLOP_PER_POINT = 10.89e6 + 65.5e3      # per 16-pair sample + feature_proj per keypoint
+# BASELINE.json configs; algorithmic FLOPs per tile from SURVEY.md §8d (encoder + decoder), TopoNet added per point
+WORKLOADS = {
+    "c1": dict(name="toponet_vitb_256", cfg=dict(_BASE, SAM_VERSION="vit_b", PATCH_SIZE=256), points=0,
+               flop_tile=46.33e9, metric="256x256 ViT-B tiles/sec",
+               note="encoder + mask head only (the reference's CPU-runnable case), 64 tiles per step"),
+    "c2": dict(name="toponet_vitb_512_cityscale", cfg=dict(_BASE, SAM_VERSION="vit_b", PATCH_SIZE=512),
+               points=256, flop_tile=195.34e9, metric="512x512 ViT-B tiles/sec",
+               note="encoder + decoder + TopoNet, 256 keypoints x 16 pairs per tile"),
+    "c3": dict(name="toponet_vitb_256_spacenet", cfg=dict(_BASE, SAM_VERSION="vit_b", PATCH_SIZE=256),
+               points=64, flop_tile=46.33e9, metric="256x256 ViT-B tiles/sec",
+               note="encoder + decoder + TopoNet, 64 keypoints x 16 pairs per tile"),
+    "c4": dict(name="toponet_vitb_512_cityscale_8x8", cfg=dict(_BASE, SAM_VERSION="vit_b", PATCH_SIZE=512),
+               points=1024, flop_tile=195.34e9, metric="512x512 ViT-B tiles/sec",
+               note="dense TopoNet: 1024 keypoints x 16 pairs per tile (16 384 sequences of 16)"),
+    "c5": dict(name="toponet_vith_256", cfg=dict(_BASE, SAM_VERSION="vit_h", PATCH_SIZE=256), points=0,
+               flop_tile=330.98e9, metric="256x256 ViT-H tiles/sec",
+               note="ViT-H encoder + mask head (head_dim 80)"),
+    "c2_samdec": dict(name="toponet_vitb_512_cityscale + USE_SAM_DECODER",
+                      cfg=dict(_BASE, SAM_VERSION="vit_b", PATCH_SIZE=512, USE_SAM_DECODER=True), points=256,
+                      flop_tile=194.50e9 + 0.91e9, metric="512x512 ViT-B tiles/sec",
+                      note="SAM TwoWayTransformer mask decoder instead of the naive decoder"),
+}
+# scene-level legs (e2e_scene): the grids of the reference's inference configs
+SCENES = {
+    "c2": [dict(tag="cityscale_2048_16x16", size=2048, per_edge=16, margin=64)],
+    "c3": [dict(tag="spacenet_400_16x16", size=400, per_edge=16, margin=0)],
+    "c4": [dict(tag="cityscale_2048_8x8", size=2048, per_edge=8, margin=64)],
+}
+SCENE_KEYS = dict(TOPO_THRESHOLD=0.5, ITSC_NMS_RADIUS=8, ROAD_NMS_RADIUS=16, NEIGHBOR_RADIUS=64,
+                  MAX_NEIGHBOR_QUERIES=16)
 
-# algorithmic FLOPs per tile: encoder 194.50 G + naive decoder 0.84 G, TopoNet
-# 10.89 MFLOP per 16-pair sample + 65.5 kFLOP per keypoint
-FLOP_PER_TILE = 195.34e9 + POINTS_PER_TILE * (10.89e6 + 65.5e3)
+
+def flop_per_tile(w):
+    return w["flop_tile"] + w["points"] * TOPO_FLOP_PER_POINT
 
 
 def load_peaks():
@@ -50,6 +82,20 @@ def load_peaks():
                     hbm=float(p["hbm_gbs"]), source="measured (MEASURED_PEAKS.json, sustained)")
     return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0,
                 source="fallback (B200_PROFILING.md)")
+
+
+def load_ncu_metrics():
+    """Per-kernel-class ncu numbers (DRAM bytes per launch, tensor-pipe %) written by tools/ncu_extract.py
+    from the `--set full` captures of tools/gpu/profile_r02.sh, stamped with the digest of the kernel sources
+    they were taken from.  Returned only when that digest is the one of the library being run."""
+    path = os.path.join(ROOT, "profiles", "ncu_metrics.json")
+    dig = os.path.join(ROOT, "sam_road_b200", "_build", "digest.txt")
+    if not (os.path.exists(path) and os.path.exists(dig)):
+        return None, "no profiles/ncu_metrics.json for this build"
+    m = json.load(open(path))
+    if m.get("digest") != open(dig).read().strip():
+        return None, "profiles/ncu_metrics.json was captured from other kernel sources (digest differs)"
+    return m, m.get("source", "profiles/ncu_metrics.json")
 
 
 class ClockSampler:
@@ -135,17 +181,19 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(self.rows), "source": self.source}
 
 
+
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle (CPU port of the reference algorithm) on host cores
 # ------------------------------------------------------------------------------------------------
-def time_cpu_oracle(n_tiles: int, steps: int, warmup: int):
+def time_cpu_oracle(w, n_tiles: int, steps: int, warmup: int):
     import torch
     from oracle import samroad_oracle as O          # the only place bench.py executes oracle/
     from sam_road_b200 import synth
-    spec = O.ModelSpec.from_config(CONFIG)
-    sd = synth.make_state_dict(CONFIG, seed=0)
-    rgb = synth.make_tiles(n_tiles, 512, seed=11, dtype=torch.float32)
-    pts, prs, val = synth.make_topo_inputs(n_tiles, 512, POINTS_PER_TILE, seed=12, ragged=False)
+    cfg, P, NP = w["cfg"], w["cfg"]["PATCH_SIZE"], w["points"]
+    spec = O.ModelSpec.from_config(cfg)
+    sd = synth.make_state_dict(cfg, seed=0)
+    rgb = synth.make_tiles(n_tiles, P, seed=11, dtype=torch.float32)
+    topo = synth.make_topo_inputs(n_tiles, P, NP, seed=12, ragged=False) if NP else None
     # all the host threads the process can really use: the affinity mask / cgroup quota may be far
     # below os.cpu_count() on a shared box, and oversubscribed eager PyTorch is several times slower,
     # so probe a few thread counts on one tile and keep the fastest
@@ -173,31 +221,32 @@ def time_cpu_oracle(n_tiles: int, steps: int, warmup: int):
         for i in range(warmup + steps):
             t0 = time.perf_counter()
             _, feat = O.infer_masks_and_img_features(sd, spec, rgb)
-            O.infer_toponet(sd, spec, feat, pts, prs, val)
+            if topo:
+                O.infer_toponet(sd, spec, feat, *topo)
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
     total = sum(times)
     return dict(value=n_tiles * len(times) / total, ms_per_step=1e3 * total / len(times), cores=cores,
-                sample=f"{n_tiles} tiles of 512x512 + TopoNet ({POINTS_PER_TILE} keypoints x 16 pairs) "
-                       f"per step, {len(times)} timed steps after {warmup} warm-up, fp32, "
+                sample=f"{n_tiles} tiles of {P}x{P}" + (f" + TopoNet ({NP} keypoints x 16 pairs)" if NP else "") +
+                       f" per step, {len(times)} timed steps after {warmup} warm-up, fp32, "
                        f"torch.set_num_threads({cores})")
 
 
-def run_reference(args):
+def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = time_cpu_oracle(n_tiles=args.ref_tiles, steps=args.steps, warmup=args.warmup)
+    r = time_cpu_oracle(w, n_tiles=args.ref_tiles, steps=args.steps, warmup=args.warmup)
     line = {
-        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "tiles/s",
+        "impl": "reference", "metric": w["metric"], "value": r["value"], "unit": "tiles/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "tiles_per_step": args.ref_tiles,
-                   "points_per_tile": POINTS_PER_TILE, "pairs_per_point": 16,
-                   "note": "reference algorithm (oracle port, fp32 PyTorch eager) on host CPU cores; "
-                           "each step is a bounded sample of the workload"},
+        "config": {"workload": w["name"], "tiles_per_step": args.ref_tiles,
+                   "points_per_tile": w["points"], "pairs_per_point": 16,
+                   "note": "reference algorithm (oracle port pinned against the unmodified reference, fp32 "
+                           "PyTorch eager) on host CPU cores; each step is a bounded sample of the workload"},
         "cpu_baseline": {"value": r["value"], "unit": "tiles/s", "cores": r["cores"], "kind": "port",
                          "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": "tiles/s", "h2d_bytes_per_step": 0,
@@ -210,7 +259,77 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # native arm
 # ------------------------------------------------------------------------------------------------
-def run_native(args):
+def _mem_line(tag, dev):
+    import torch
+    free, total = torch.cuda.mem_get_info(dev)
+    try:
+        import psutil
+        rss = psutil.Process().memory_info().rss / 2**30
+        avail = psutil.virtual_memory().available / 2**30
+    except Exception:
+        rss = avail = float("nan")
+    sys.stderr.write(f"[bench mem] {tag}: rank {os.environ.get('RANK', '0')} device used "
+                     f"{(total - free) / 2**30:.1f} GiB of {total / 2**30:.0f} (torch reserved "
+                     f"{torch.cuda.memory_reserved(dev) / 2**30:.1f}), host rss {rss:.1f} GiB, host available "
+                     f"{avail:.0f} GiB\n")
+    sys.stderr.flush()
+
+
+def run_scenes(args, w, wl, dev, rank, world, barrier):
+    """e2e_scene: `infer_one_img` on whole synthetic scenes.  Thresholds are set from the scene's own
+    fused masks (random weights give noise-like masks) so that ~0.4 % of the pixels are intersection
+    candidates and ~5 % road candidates, the density of a real road mask."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from sam_road_b200 import SAMRoad, synth
+    from sam_road_b200.inferencer import infer_one_img
+    out = {}
+    for sc in SCENES.get(wl, []):
+        cfg = dict(w["cfg"], SAMPLE_MARGIN=sc["margin"], INFER_PATCHES_PER_EDGE=sc["per_edge"], **SCENE_KEYS,
+                   ITSC_THRESHOLD=2.0, ROAD_THRESHOLD=2.0)
+        net = SAMRoad(cfg)
+        net.load_state_dict(synth.make_state_dict(cfg, seed=0, logit_gain=6.0), strict=True)
+        net.eval().to(dev)
+        img = np.random.RandomState(17).randint(0, 256, size=(sc["size"], sc["size"], 3)).astype(np.uint8)
+        _, _, kp, road = infer_one_img(net, img, cfg, device=dev)       # probe: masks only (also the warm-up)
+        cfg.update(ITSC_THRESHOLD=float(np.quantile(kp, 0.996)) / 255, ROAD_THRESHOLD=float(np.quantile(road, 0.95)) / 255)
+        n_tiles = sc["per_edge"] ** 2
+        res = {"scene": f"{sc['size']}x{sc['size']} uint8, {n_tiles} tiles of {cfg['PATCH_SIZE']}^2, margin {sc['margin']}, "
+                        f"INFER_BATCH_SIZE {cfg['INFER_BATCH_SIZE']}", "unit": "tiles/s",
+               "h2d_bytes_per_scene": int(img.nbytes)}
+        for tie in ("numpy", "stable"):
+            tm = {}
+            infer_one_img(net, img, cfg, device=dev, nms_tie_order=tie, timings=tm)      # warm-up + stage split
+            times = []
+            for _ in range(args.scene_runs):
+                barrier()
+                t0 = time.perf_counter()
+                nodes, edges, kp, road = infer_one_img(net, img, cfg, device=dev, nms_tie_order=tie)
+                barrier()
+                times.append(time.perf_counter() - t0)
+            sec = sorted(times)[len(times) // 2]
+            if world > 1:
+                t = torch.tensor([sec], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                sec = t.item()
+            res[tie] = {"value": n_tiles / sec, "ms_per_scene": 1e3 * sec, "runs": len(times),
+                        "n_points": int(nodes.shape[0]), "n_edges": int(edges.shape[0]),
+                        "d2h_bytes_per_scene": int(kp.nbytes + road.nbytes + nodes.nbytes + edges.nbytes),
+                        "stages_ms": {k: round(1e3 * v, 3) for k, v in tm.items() if k.endswith("_s")},
+                        "graph_stats": {k: v for k, v in tm.get("graph_stats", {}).items()},
+                        "topo_samples": tm.get("topo_samples")}
+        res["value"] = res["numpy"]["value"]
+        res["note"] = ("'numpy': this host's np.argsort decides the visiting order of equal scores in the greedy "
+                       "NMS (bit-exact with the reference on this host); 'stable': device-only sort")
+        res["scaling"] = "strong (one scene sharded over the ranks)" if world > 1 else "single GPU"
+        out[sc["tag"]] = res
+        del net
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_native(args, w, wl):
     import torch
     import torch.distributed as dist
     from sam_road_b200 import SAMRoad, _lib, synth
@@ -224,36 +343,56 @@ def run_native(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # the all-gathers run beside the next step's compute: keep NCCL's footprint on the SMs small
+        os.environ.setdefault("NCCL_MAX_CTAS", "8")
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
-    B, P, NP = args.batch, 512, POINTS_PER_TILE
+    CONFIG = w["cfg"]
+    B, P, NP = args.batch, CONFIG["PATCH_SIZE"], w["points"]
+    FLOP_PER_TILE = flop_per_tile(w)
 
     net = SAMRoad(CONFIG)
     net.load_state_dict(synth.make_state_dict(CONFIG, seed=0), strict=True)
     net.eval().to(dev)
 
-    # R distinct resident input batches: R * 50 MB of uint8 tiles > L2 (126 MB); the step's own
-    # activations (>1 GB) also exceed L2 many times over, so no explicit L2 flush is needed.
+    # R distinct resident input batches: R * B * P^2 * 3 B of uint8 tiles; the step's own activations
+    # (>1 GB at 64 tiles of 512^2) exceed the 126 MB L2 many times over, so no explicit flush is needed.
     R = 3
     tiles = [synth.make_tiles(B, P, seed=100 * rank + r).to(dev) for r in range(R)]
-    topo_host = [synth.make_topo_inputs(B, P, NP, seed=100 * rank + r, ragged=False) for r in range(R)]
-    topo = [[t.to(dev) for t in th] for th in topo_host]
+    topo_host = [synth.make_topo_inputs(B, P, NP, seed=100 * rank + r, ragged=False) for r in range(R)] if NP else None
+    topo = [[t.to(dev) for t in th] for th in topo_host] if NP else None
 
+    # exchange step of the path: per-tile mask scores and topology scores to every rank.
+    # Double-buffered and issued asynchronously: step i's all-gathers run under step i+1's compute.
     gather_sc = gather_ts = None
+    pending = []
     if world > 1:
-        gather_sc = torch.empty((world * B, P, P, 2), dtype=torch.float32, device=dev)
-        gather_ts = torch.empty((world * B, NP, 16, 1), dtype=torch.float32, device=dev)
+        gather_sc = [torch.empty((world * B, P, P, 2), dtype=torch.float32, device=dev) for _ in range(2)]
+        if NP:
+            gather_ts = [torch.empty((world * B, NP, 16, 1), dtype=torch.float32, device=dev) for _ in range(2)]
+    _mem_line("native arm, inputs resident", dev)
 
     def step(i):
         r = i % R
         scores, feat = net.infer_masks_and_img_features(tiles[r])
-        ts = net.infer_toponet(feat, *topo[r])
-        if world > 1:   # the path's exchange step: per-tile mask + topology scores
-            dist.all_gather_into_tensor(gather_sc, scores)
-            dist.all_gather_into_tensor(gather_ts, ts)
+        ts = net.infer_toponet(feat, *topo[r]) if NP else None
+        if world > 1:
+            while len(pending) >= 2:                       # buffer (i % 2) is free once step i-2's gathers are done
+                for wk in pending.pop(0)[0]:
+                    wk.wait()
+            works = [dist.all_gather_into_tensor(gather_sc[i % 2], scores, async_op=True)]
+            if NP:
+                works.append(dist.all_gather_into_tensor(gather_ts[i % 2], ts, async_op=True))
+            pending.append((works, scores, ts))            # keep the sources alive until the collective has read them
         return scores, ts
 
+    def drain():
+        while pending:
+            for wk in pending.pop(0)[0]:
+                wk.wait()
+
     def barrier():
+        drain()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -272,6 +411,7 @@ def run_native(args):
         e0.record()
         for i in range(args.steps):
             step(args.warmup + i)
+        drain()                                            # the last steps' gathers belong to the timed region
         e1.record()
         barrier()
     launches = int(lib.samroad_launch_count(0))
@@ -289,25 +429,37 @@ def run_native(args):
     # ---- e2e: the host-buffer C-ABI call, pinned host tiles in, results out, every step ----------
     h_tiles = [t.cpu().pin_memory() for t in tiles]
     h_topo = [[t.contiguous().pin_memory() for t in (th[0], th[1], th[2].view(torch.uint8))]
-              for th in topo_host]
-    h_scores = torch.empty((B, P, P, 2), dtype=torch.float32).pin_memory()
-    h_emb = torch.empty((B, 256, P // 16, P // 16), dtype=torch.float32).pin_memory()
-    h_ts = torch.empty((B, NP, 16), dtype=torch.float32).pin_memory()
+              for th in topo_host] if NP else None
+    del tiles, topo, gather_sc, gather_ts               # the e2e leg owns its own (staged) device buffers
+    torch.cuda.empty_cache()
+    h_scores = [torch.empty((B, P, P, 2), dtype=torch.float32).pin_memory() for _ in range(2)]
+    h_emb = [torch.empty((B, 256, P // 16, P // 16), dtype=torch.float32).pin_memory() for _ in range(2)]
+    h_ts = [torch.empty((B, max(NP, 1), 16), dtype=torch.float32).pin_memory() for _ in range(2)]
+    _mem_line("native arm, e2e leg", dev)
 
-    def e2e_step(i):
-        r = i % R
-        p, q, v = h_topo[r]
-        _lib.check(lib.samroad_infer_batch_host(
-            handle, h_tiles[r].data_ptr(), _lib.U8, B, p.data_ptr(), _lib.I64, q.data_ptr(), _lib.I64,
-            v.data_ptr(), NP, NP, 16, h_scores.data_ptr(), h_emb.data_ptr(), h_ts.data_ptr()),
-            "samroad_infer_batch_host")
+    def e2e_submit(i):
+        r, sl = i % R, i % 2
+        if NP:
+            p, q, v = h_topo[r]
+            pp, qp, vp, ts = p.data_ptr(), q.data_ptr(), v.data_ptr(), h_ts[sl].data_ptr()
+        else:
+            pp = qp = vp = ts = None
+        _lib.check(lib.samroad_infer_batch_host_async(
+            handle, sl, h_tiles[r].data_ptr(), _lib.U8, B, pp, _lib.I64, qp, _lib.I64, vp, NP, NP, 16,
+            h_scores[sl].data_ptr(), h_emb[sl].data_ptr(), ts), "samroad_infer_batch_host_async")
 
-    for i in range(max(1, min(2, args.warmup))):
-        e2e_step(i)
+    def e2e_run(n, first):
+        # a streaming consumer: batch i is submitted, then batch i-1's results are awaited and "read"
+        for i in range(n):
+            e2e_submit(first + i)
+            if i >= 1:
+                _lib.check(lib.samroad_infer_batch_host_wait(handle, (first + i - 1) % 2), "wait")
+        _lib.check(lib.samroad_infer_batch_host_wait(handle, (first + n - 1) % 2), "wait")
+
+    e2e_run(max(2, min(3, args.warmup)), 0)
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        e2e_step(i)
+    e2e_run(args.steps, 0)
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -315,8 +467,15 @@ def run_native(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = t.item()
     e2e_value = world * B * args.steps / e2e_s
-    h2d = sum(x.numel() * x.element_size() for x in (h_tiles[0], *h_topo[0]))
-    d2h = sum(x.numel() * x.element_size() for x in (h_scores, h_emb, h_ts))
+    h2d = sum(x.numel() * x.element_size() for x in ((h_tiles[0], *h_topo[0]) if NP else (h_tiles[0],)))
+    d2h = sum(x.numel() * x.element_size() for x in ((h_scores[0], h_emb[0], h_ts[0]) if NP else (h_scores[0], h_emb[0])))
+    del net
+    torch.cuda.empty_cache()
+
+    # ---- e2e_scene: whole scenes through infer_one_img -----------------------------------------------
+    scenes = None
+    if not args.no_scene:
+        scenes = run_scenes(args, w, wl, dev, rank, world, barrier)
 
     if rank != 0:
         if world > 1:
@@ -324,13 +483,8 @@ def run_native(args):
         return
 
     # ---- roofline of the dominant kernel class ---------------------------------------------------
-    # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernel classes captured
-    # with `ncu --set full` at this workload: profiles/r01_gemm_f16_v4_raw.csv, r01_gemm_resid_v4_raw.csv
-    # (proj: r01_gemm_resid_v3_raw.csv), r01_att_v6_raw.csv (tools/gpu/profile_r01.sh).  Only valid for
-    # the default batch of 64 tiles.
-    ncu_traffic = {"gemm_mlp_lin1": 105.514240e6 + 347.093760e6, "gemm_qkv": 104.339456e6 + 245.466624e6,
-                   "gemm_mlp_lin2": 614.097152e6 + 172.180992e6, "gemm_proj": 303.192576e6 + 143.959552e6,
-                   "attention_global": 302.231040e6 + 80.478464e6, "attention_window": 302.097664e6 + 78.441216e6}
+    ncu, ncu_src = load_ncu_metrics()
+    ncu_ok = ncu is not None and args.batch == 64 and wl == ncu.get("workload", "c2")
     peaks = load_peaks()
     gemm_like = {k: v for k, v in kernels.items() if v["flops"] > 0}
     dom = max(gemm_like, key=lambda k: gemm_like[k]["ms"]) if gemm_like else None
@@ -341,8 +495,8 @@ def run_native(args):
         achieved = d["flops"] / d["launches"] / (per_launch_ms * 1e-3) / 1e12
         roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"],
                     "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                    "traffic": ncu_traffic.get(dom) if args.batch == 64 else None,
-                    "traffic_source": "ncu --set full, profiles/r01_*_raw.csv (bytes per launch)",
+                    "traffic": (ncu["kernels"].get(dom, {}).get("dram_bytes_per_launch") if ncu_ok else None),
+                    "traffic_source": ncu_src if ncu_ok else f"not reported: {ncu_src}",
                     "peak_source": peaks["source"], "launches": d["launches"],
                     "avg_launch_ms": per_launch_ms,
                     "algorithmic_flops_per_launch": d["flops"] / d["launches"]}
@@ -355,35 +509,37 @@ def run_native(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        r = time_cpu_oracle(n_tiles=2, steps=3, warmup=1)
+        r = time_cpu_oracle(w, n_tiles=2, steps=3, warmup=1)
         cpu = {"value": r["value"], "unit": "tiles/s", "cores": r["cores"], "kind": "port",
                "sample": r["sample"]}
 
     line = {
-        "metric": METRIC, "value": value, "unit": "tiles/s", "n_gpus": world, "steps": args.steps,
+        "metric": w["metric"], "value": value, "unit": "tiles/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "tiles_per_step_per_gpu": B, "patch_size": P,
-                   "points_per_tile": NP, "pairs_per_point": 16, "input_dtype": "uint8",
-                   "l2_policy": f"{R} rotating resident input batches (> L2) and >1 GB of "
-                                "activations per step; no explicit flush",
+        "config": {"workload": w["name"], "workload_key": wl, "what": w["note"], "tiles_per_step_per_gpu": B,
+                   "patch_size": P, "points_per_tile": NP, "pairs_per_point": 16, "input_dtype": "uint8",
+                   "l2_policy": f"{R} rotating resident input batches and >1 GB of activations per step "
+                                "(> 126 MB L2); no explicit flush",
                    "parallelism": f"tile-sharded dp{world}" +
-                                  (" + all_gather(mask scores, topo scores)" if world > 1 else "")},
+                                  (" + async all_gather(mask scores, topo scores) overlapped with the next step"
+                                   if world > 1 else "")},
         "e2e": {"value": e2e_value, "unit": "tiles/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps,
-                "call": "samroad_infer_batch_host (pinned host uint8 tiles -> mask scores, "
-                        "embeddings, topology scores on host)", "timer": "perf_counter"},
+                "call": "samroad_infer_batch_host_async / _wait, two staging slots (pinned host uint8 tiles -> mask "
+                        "scores, embeddings, topology scores on host; batch i's downloads overlap batch i+1)",
+                "timer": "perf_counter"},
+        "e2e_scene": scenes,
         "gpu_launches": launches,
         "clocks": clocks.summary(),
         "roofline": roofline,
         "path_tensor_frac": value / world * FLOP_PER_TILE / 1e12 / peaks["tflops"],
         "algorithmic_gflop_per_tile": FLOP_PER_TILE / 1e9,
-        # BASELINE's third metric: sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active of the
-        # dominant kernels from the committed ncu --set full captures (not measured in this run)
-        "tensor_pipe_pct_ncu": {"gemm_qkv": 72.5, "gemm_mlp_lin1": 66.6, "gemm_mlp_lin2": 79.8,
-                                "attention_global": 22.3, "attention_window": 19.2,
-                                "source": "profiles/r01_ncu_summary_v4.md"},
+        # BASELINE's third metric: sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active per kernel class
+        # from the committed ncu --set full captures of THIS build (null when the captures are of another build)
+        "tensor_pipe_pct_ncu": ({k: v.get("tensor_pipe_pct") for k, v in ncu["kernels"].items()} if ncu_ok else None),
+        "tensor_pipe_pct_source": ncu_src,
         "kernels": shares,
         "cpu_baseline": cpu,
     }
@@ -429,19 +585,24 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--batch", type=int, default=CONFIG["INFER_BATCH_SIZE"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS),
+                    help="BASELINE.json configuration (default c2 = toponet_vitb_512_cityscale)")
+    ap.add_argument("--batch", type=int, default=64, help="tiles per step per GPU (INFER_BATCH_SIZE)")
     ap.add_argument("--ref-tiles", type=int, default=4,
                     help="tiles per step of the CPU reference arm (bounded sample)")
+    ap.add_argument("--scene-runs", type=int, default=5, help="timed infer_one_img runs per scene and tie order")
+    ap.add_argument("--no-scene", action="store_true", help="skip the e2e_scene legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--debug-gemm-mode", type=int, default=0,
                     help="A/B only: samroad_debug_disable_2cta_gemm bit mask (16 = no snake traversal)")
     args = ap.parse_args()
+    w = WORKLOADS[args.workload]
     with _JsonStdout() as out:
         _OUT = out
         if args.impl == "reference":
-            run_reference(args)
+            run_reference(args, w)
         else:
-            run_native(args)
+            run_native(args, w, args.workload)
 
 
 if __name__ == "__main__":

@@ -170,6 +170,18 @@ int samroad_aggregate_edges(samroad_graph_t g, const float* topo_scores,
                             const int64_t* tile_score_offset_host, int K, float threshold,
                             int64_t* edges, int cap, int* n_edges, int* bad_score, void* stream);
 
+/* The pipelined form of samroad_infer_batch_host: queue one batch on staging slot 0 or 1 and return;
+ * samroad_infer_batch_host_wait(h, slot) blocks until that batch's results are in host memory.  With
+ * the two slots alternating, the downloads of batch i overlap the upload and the compute of batch
+ * i+1 (what a scene driver streaming batches does).  Host buffers must stay valid (and should be
+ * page-locked) until the wait returns. */
+int samroad_infer_batch_host_async(samroad_handle_t h, int slot, const void* rgb_host, int rgb_dtype,
+                                   int B, const void* points_host, int pts_dtype,
+                                   const void* pairs_host, int pairs_dtype, const uint8_t* valid_host,
+                                   int N, int Ns, int Np, float* mask_scores_host,
+                                   float* image_embeddings_host, float* topo_scores_host);
+int samroad_infer_batch_host_wait(samroad_handle_t h, int slot);
+
 /* Per-kernel-class CUDA-event timing on the launching stream (bench.py's roofline numbers).
  * samroad_timing_enable(h, 1) clears and starts recording; samroad_timing_read() synchronises and
  * writes a JSON object {"<class>": {"launches","ms","flops","bytes"}, ...} into buf. */
@@ -220,6 +232,9 @@ void samroad_debug_force_simt_attention(int on);
  * epilogue (bit-identical to the register path) instead of the default TMA reduce-add; bit 4 makes
  * every encoder kernel walk the token rows in ascending order (no snake traversal). */
 void samroad_debug_disable_2cta_gemm(int off);
+/* Test hook: direction in which the next op-level row-streaming kernel (LayerNorm, 2-CTA GEMM, encoder
+ * attention) walks the token rows (1 = descending; the encoder alternates it from kernel to kernel). */
+void samroad_debug_set_traverse_reverse(int on);
 /* Debug hook: device buffer of 256 int64 receiving clock64 stamps of CTA 0's first work unit in the
  * tcgen05 attention kernel (softmax warp phases, MMA issue times); NULL disables. */
 void samroad_debug_attention_trace(void* dev_buf);

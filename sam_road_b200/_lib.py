@@ -57,6 +57,9 @@ SIGNATURES = {
     "samroad_aggregate_edges": (_i, [_vp, _vp, _vp, _i, _f, _vp, _i, _ip, _ip, _vp]),
     "samroad_encode_masks_host": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "samroad_infer_batch_host": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "samroad_infer_batch_host_async": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _vp,
+                                            _vp]),
+    "samroad_infer_batch_host_wait": (_i, [_vp, _i]),
     "samroad_timing_enable": (_i, [_vp, _i]),
     "samroad_timing_read": (_i, [_vp, C.c_char_p, C.c_size_t]),
     "samroad_workspace_bytes": (C.c_size_t, [_vp, _i]),
@@ -71,6 +74,7 @@ SIGNATURES = {
     "samroad_op_layernorm": (_i, [_vp, _vp, _vp, _f, _i, _i, _vp, _vp]),
     "samroad_debug_force_simt_attention": (None, [_i]),
     "samroad_debug_disable_2cta_gemm": (None, [_i]),
+    "samroad_debug_set_traverse_reverse": (None, [_i]),
     "samroad_debug_attention_trace": (None, [_vp]),
     "samroad_op_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
 }

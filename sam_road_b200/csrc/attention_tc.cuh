@@ -399,7 +399,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     const uint32_t tO = tmem_base + tlane + 256 + g * 64;
     const uint32_t tT = tmem_base + tlane + 384 + g * 64;      // kSepT only
     uint8_t* myP = sP + g * 32768 + row * 128;
-    float* scratch = reinterpret_cast<float*>(sP + g * 32768);   // [HALF][128] gather scratch
+    // Gather scratch of the rel-pos projection: THREAD-PRIVATE, inside the thread's own two P rows (row
+    // `row` of k-block 0 holds table rows 0..31, of k-block 1 rows 32..63), rotated by the lane so that a
+    // warp's accesses hit 32 banks.  (A group-wide [HALF][128] scratch over the P buffer let a warp that is
+    // late into a unit scribble over the P rows an early warp had already stored for the unit's first
+    // block -- a rare, schedule-dependent corruption; window units with idle warps made the skew large.)
+    auto scr = [&](int j) -> float* {
+      return reinterpret_cast<float*>(myP + (j >> 5) * 16384) + ((j + lane) & 31);
+    };
     const int sw = row & 7;
     constexpr float kLog2e = 1.4426950408889634f;
     int bcnt = 0;                                  // blocks completed by this group in earlier units
@@ -462,7 +469,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             uint32_t r32[32];
             tmem_ld_32x32((kSepT ? tT : tS) + half * HALF + c * 32, r32);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) scratch[(c * 32 + i) * 128 + row] = __uint_as_float(r32[i]);
+            for (int i = 0; i < 32; ++i) *scr(c * 32 + i) = __uint_as_float(r32[i]);
           }
           if (half == 1) {
             tc_fence_before_sync();
@@ -471,7 +478,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
           const int sh = (half == 0 ? sy : sx) + WIN - 1;
 #pragma unroll
           for (int i = 0; i < WIN; ++i) {
-            const float v = scratch[(sh - i) * 128 + row] * kLog2e;
+            const float v = *scr(sh - i) * kLog2e;
             if (half == 0) rel_h[i] = v; else rel_w[i] = v;
           }
         }

@@ -323,7 +323,11 @@ attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     const uint32_t tlane = static_cast<uint32_t>(quarter * 32) << 16;
     const uint32_t tS = tmS + tlane, tO = tmO + tlane, tT = tmT + tlane;
     uint8_t* myP = sP + row * 128;
-    float* scratch = reinterpret_cast<float*>(sP);               // [HALF][128] gather scratch
+    // Gather scratch of the rel-pos projection: thread-private, inside the thread's own two P rows, rotated
+    // by the lane (see attention_tc.cuh: a group-wide scratch over the P buffer raced with early P stores)
+    auto scr = [&](int j) -> float* {
+      return reinterpret_cast<float*>(myP + (j >> 5) * 16384) + ((j + lane) & 31);
+    };
     const int sw = row & 7;
     constexpr float kLog2e = 1.4426950408889634f;
     int bcnt = 0, tcnt = 0;
@@ -385,7 +389,7 @@ attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
               uint32_t r32[32];
               tmem_ld_32x32(tT + half * HALF + c * 32, r32);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) scratch[(c * 32 + i) * 128 + row] = __uint_as_float(r32[i]);
+              for (int i = 0; i < 32; ++i) *scr(c * 32 + i) = __uint_as_float(r32[i]);
             }
             if (half == 1) {
               tc_fence_before_sync();
@@ -394,7 +398,7 @@ attention_tc80_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
             const int sh = (half == 0 ? sy : sx) + WIN - 1;
 #pragma unroll
             for (int i = 0; i < WIN; ++i) {
-              const float v = scratch[(sh - i) * 128 + row] * kLog2e;
+              const float v = *scr(sh - i) * kLog2e;
               if (half == 0) rel_h[i] = v; else rel_w[i] = v;
             }
           }

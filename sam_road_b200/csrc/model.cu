@@ -127,13 +127,17 @@ struct samroad_ctx {
   // activation workspace (grown on demand)
   void* ws = nullptr;
   size_t ws_bytes = 0;
-  // staging for the host-buffer entry point
-  void* stage_in = nullptr;  size_t stage_in_bytes = 0;
-  cudaStream_t s_compute = nullptr, s_copy = nullptr;   // host-buffer entry point: compute / D2H overlap
-  cudaEvent_t ev_emb = nullptr, ev_scores = nullptr;
-  bool hook_after_neck = false;                          // record ev_emb once the embeddings are final
-  float* stage_scores = nullptr; size_t stage_scores_bytes = 0;
-  float* stage_emb = nullptr; size_t stage_emb_bytes = 0;
+  // staging for the host-buffer entry points: two slots so that step i's downloads overlap step
+  // i+1's upload and compute (samroad_infer_batch_host_async / _wait)
+  struct HostSlot {
+    void* in = nullptr;  size_t in_bytes = 0;           // tiles + TopoNet inputs + topology scores
+    float* scores = nullptr; size_t scores_bytes = 0;
+    float* emb = nullptr; size_t emb_bytes = 0;
+    cudaEvent_t ev_h2d = nullptr, ev_emb = nullptr, ev_scores = nullptr, ev_compute = nullptr, ev_done = nullptr;
+  };
+  HostSlot slots[2];
+  cudaStream_t s_h2d = nullptr, s_compute = nullptr, s_copy = nullptr;   // upload / compute / download
+  cudaEvent_t ev_emb_hook = nullptr;                     // recorded once the embeddings are final (after the neck)
 };
 
 namespace {
@@ -396,11 +400,14 @@ extern "C" int samroad_destroy(samroad_handle_t h) {
   for (void* p : h->weight_allocs) cudaFree(p);
   if (h->ws) cudaFree(h->ws);
   if (h->sam_ws) cudaFree(h->sam_ws);
-  if (h->s_compute) { cudaStreamDestroy(h->s_compute); cudaStreamDestroy(h->s_copy);
-                      cudaEventDestroy(h->ev_emb); cudaEventDestroy(h->ev_scores); }
-  if (h->stage_in) cudaFree(h->stage_in);
-  if (h->stage_scores) cudaFree(h->stage_scores);
-  if (h->stage_emb) cudaFree(h->stage_emb);
+  if (h->s_compute) { cudaStreamDestroy(h->s_h2d); cudaStreamDestroy(h->s_compute); cudaStreamDestroy(h->s_copy); }
+  for (auto& sl : h->slots) {
+    if (sl.in) cudaFree(sl.in);
+    if (sl.scores) cudaFree(sl.scores);
+    if (sl.emb) cudaFree(sl.emb);
+    for (cudaEvent_t e : {sl.ev_h2d, sl.ev_emb, sl.ev_scores, sl.ev_compute, sl.ev_done})
+      if (e) cudaEventDestroy(e);
+  }
   delete h;
   return 0;
 }
@@ -787,7 +794,7 @@ extern "C" int samroad_encode_masks(samroad_handle_t h, const void* rgb, int rgb
   }
 
   // naive map decoder (model.py:286-295, 490-491) as three GEMMs, pixel shuffle by row indexing
-  if (h->hook_after_neck) SRB_CUDA_OK(cudaEventRecord(h->ev_emb, st));   // embeddings are final here
+  if (h->ev_emb_hook) SRB_CUDA_OK(cudaEventRecord(h->ev_emb_hook, st));   // embeddings are final here
   if ((mask_scores || mask_logits) && h->cfg.use_sam_decoder) {
     // SAM mask decoder (model.py:471-488): null prompts, TwoWayTransformer, upscaler, x4 bilinear
     SRB_TRY(ensure_bytes(&h->sam_ws, &h->sam_ws_bytes, sam_decoder_ws_bytes(B, T)));
@@ -828,29 +835,8 @@ extern "C" int samroad_encode_masks_scene(samroad_handle_t h, const uint8_t* sce
 extern "C" int samroad_encode_masks_host(samroad_handle_t h, const void* rgb_host, int rgb_dtype,
                                          int B, float* mask_scores_host,
                                          float* image_embeddings_host) {
-  SRB_TRY(check_handle(h, true));
-  SRB_REQUIRE(rgb_host, "samroad_encode_masks_host: null rgb");
-  if (B <= 0) return 0;
-  const size_t P = h->cfg.patch_size, s = h->s;
-  const size_t in_bytes = static_cast<size_t>(B) * P * P * 3 * (rgb_dtype == SAMROAD_U8 ? 1 : 4);
-  const size_t sc_bytes = static_cast<size_t>(B) * P * P * 2 * 4;
-  const size_t em_bytes = static_cast<size_t>(B) * 256 * s * s * 4;
-  SRB_TRY(ensure_bytes(&h->stage_in, &h->stage_in_bytes, in_bytes));
-  SRB_TRY(ensure_bytes(reinterpret_cast<void**>(&h->stage_scores), &h->stage_scores_bytes, sc_bytes));
-  SRB_TRY(ensure_bytes(reinterpret_cast<void**>(&h->stage_emb), &h->stage_emb_bytes, em_bytes));
-  cudaStream_t st = nullptr;
-  SRB_CUDA_OK(cudaMemcpyAsync(h->stage_in, rgb_host, in_bytes, cudaMemcpyHostToDevice, st));
-  SRB_TRY(samroad_encode_masks(h, h->stage_in, rgb_dtype, B,
-                               mask_scores_host ? h->stage_scores : nullptr, nullptr, h->stage_emb,
-                               st));
-  if (mask_scores_host)
-    SRB_CUDA_OK(cudaMemcpyAsync(mask_scores_host, h->stage_scores, sc_bytes, cudaMemcpyDeviceToHost,
-                                st));
-  if (image_embeddings_host)
-    SRB_CUDA_OK(cudaMemcpyAsync(image_embeddings_host, h->stage_emb, em_bytes,
-                                cudaMemcpyDeviceToHost, st));
-  SRB_CUDA_OK(cudaStreamSynchronize(st));
-  return 0;
+  return samroad_infer_batch_host(h, rgb_host, rgb_dtype, B, nullptr, 0, nullptr, 0, nullptr, 0, 0, 0,
+                                  mask_scores_host, image_embeddings_host, nullptr);
 }
 
 // =================================================================================================
@@ -982,17 +968,20 @@ extern "C" int samroad_timing_read(samroad_handle_t h, char* buf, size_t cap) {
   return 0;
 }
 
-// One whole batch with HOST buffers: H2D tiles (+ TopoNet inputs), encoder + mask head + TopoNet,
-// D2H of mask scores, image embeddings and topology scores, then synchronise.  Any output may be
-// NULL; TopoNet is skipped when points_host is NULL.
-extern "C" int samroad_infer_batch_host(samroad_handle_t h, const void* rgb_host, int rgb_dtype,
-                                        int B, const void* points_host, int pts_dtype,
-                                        const void* pairs_host, int pairs_dtype,
-                                        const uint8_t* valid_host, int N, int Ns, int Np,
-                                        float* mask_scores_host, float* image_embeddings_host,
-                                        float* topo_scores_host) {
+// One whole batch with HOST buffers, asynchronously, on staging slot 0 or 1: H2D of the tiles (+ TopoNet
+// inputs) on an upload stream, encoder + mask head + TopoNet on the compute stream, D2H of image
+// embeddings / mask scores / topology scores on a download stream as soon as each is final.  With two
+// slots in flight the downloads of step i (202 MB at the bench workload) run under the upload and
+// the compute of step i+1.  Any output may be NULL; TopoNet is skipped when points_host is NULL.
+extern "C" int samroad_infer_batch_host_async(samroad_handle_t h, int slot, const void* rgb_host,
+                                              int rgb_dtype, int B, const void* points_host,
+                                              int pts_dtype, const void* pairs_host, int pairs_dtype,
+                                              const uint8_t* valid_host, int N, int Ns, int Np,
+                                              float* mask_scores_host, float* image_embeddings_host,
+                                              float* topo_scores_host) {
   SRB_TRY(check_handle(h, true));
   SRB_REQUIRE(rgb_host, "samroad_infer_batch_host: null rgb");
+  SRB_REQUIRE(slot == 0 || slot == 1, "samroad_infer_batch_host_async: slot %d (want 0 or 1)", slot);
   if (B <= 0) return 0;
   const size_t P = h->cfg.patch_size, s = h->s;
   const size_t in_bytes = static_cast<size_t>(B) * P * P * 3 * (rgb_dtype == SAMROAD_U8 ? 1 : 4);
@@ -1006,49 +995,81 @@ extern "C" int samroad_infer_batch_host(samroad_handle_t h, const void* rgb_host
   const size_t ts_bytes = topo ? static_cast<size_t>(B) * Ns * Np * 4 : 0;
   const size_t o_pts = align_up(in_bytes, 256), o_prs = o_pts + align_up(pts_bytes, 256);
   const size_t o_val = o_prs + align_up(prs_bytes, 256), o_ts = o_val + align_up(val_bytes, 256);
-  SRB_TRY(ensure_bytes(&h->stage_in, &h->stage_in_bytes, o_ts + align_up(ts_bytes, 256)));
-  SRB_TRY(ensure_bytes(reinterpret_cast<void**>(&h->stage_scores), &h->stage_scores_bytes, sc_bytes));
-  SRB_TRY(ensure_bytes(reinterpret_cast<void**>(&h->stage_emb), &h->stage_emb_bytes, em_bytes));
-  char* base = static_cast<char*>(h->stage_in);
-  // compute on one stream, result downloads on a second one: the embeddings go back while the mask
-  // decoder runs, the mask scores while TopoNet runs
+  samroad_ctx::HostSlot& sl = h->slots[slot];
   if (!h->s_compute) {
+    SRB_CUDA_OK(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
     SRB_CUDA_OK(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
     SRB_CUDA_OK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
-    SRB_CUDA_OK(cudaEventCreateWithFlags(&h->ev_emb, cudaEventDisableTiming));
-    SRB_CUDA_OK(cudaEventCreateWithFlags(&h->ev_scores, cudaEventDisableTiming));
   }
-  cudaStream_t st = h->s_compute, sc = h->s_copy;
-  SRB_CUDA_OK(cudaMemcpyAsync(base, rgb_host, in_bytes, cudaMemcpyHostToDevice, st));
+  if (!sl.ev_done) {
+    for (cudaEvent_t* e : {&sl.ev_h2d, &sl.ev_emb, &sl.ev_scores, &sl.ev_compute, &sl.ev_done})
+      SRB_CUDA_OK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  }
+  SRB_TRY(ensure_bytes(&sl.in, &sl.in_bytes, o_ts + align_up(ts_bytes, 256)));
+  SRB_TRY(ensure_bytes(reinterpret_cast<void**>(&sl.scores), &sl.scores_bytes, sc_bytes));
+  SRB_TRY(ensure_bytes(reinterpret_cast<void**>(&sl.emb), &sl.emb_bytes, em_bytes));
+  // the activation workspace is shared by both slots: grow it before anything is in flight on it
+  SRB_TRY(ensure_bytes(&h->ws, &h->ws_bytes, layout_enc(h, B, nullptr).total));
+  if (topo) SRB_TRY(ensure_bytes(&h->ws, &h->ws_bytes, layout_topo(B, N, Ns, Np, nullptr).total));
+  char* base = static_cast<char*>(sl.in);
+  cudaStream_t su = h->s_h2d, st = h->s_compute, sc = h->s_copy;
+  // upload: the slot's input staging was last read by the slot's previous compute
+  SRB_CUDA_OK(cudaStreamWaitEvent(su, sl.ev_compute, 0));
+  SRB_CUDA_OK(cudaMemcpyAsync(base, rgb_host, in_bytes, cudaMemcpyHostToDevice, su));
   if (topo) {
-    SRB_CUDA_OK(cudaMemcpyAsync(base + o_pts, points_host, pts_bytes, cudaMemcpyHostToDevice, st));
-    SRB_CUDA_OK(cudaMemcpyAsync(base + o_prs, pairs_host, prs_bytes, cudaMemcpyHostToDevice, st));
-    SRB_CUDA_OK(cudaMemcpyAsync(base + o_val, valid_host, val_bytes, cudaMemcpyHostToDevice, st));
+    SRB_CUDA_OK(cudaMemcpyAsync(base + o_pts, points_host, pts_bytes, cudaMemcpyHostToDevice, su));
+    SRB_CUDA_OK(cudaMemcpyAsync(base + o_prs, pairs_host, prs_bytes, cudaMemcpyHostToDevice, su));
+    SRB_CUDA_OK(cudaMemcpyAsync(base + o_val, valid_host, val_bytes, cudaMemcpyHostToDevice, su));
   }
-  h->hook_after_neck = true;
-  const int rc_enc = samroad_encode_masks(h, base, rgb_dtype, B, mask_scores_host ? h->stage_scores : nullptr,
-                                          nullptr, h->stage_emb, st);
-  h->hook_after_neck = false;
+  SRB_CUDA_OK(cudaEventRecord(sl.ev_h2d, su));
+  // compute: after the upload, and after the slot's previous results have left its output staging
+  SRB_CUDA_OK(cudaStreamWaitEvent(st, sl.ev_h2d, 0));
+  SRB_CUDA_OK(cudaStreamWaitEvent(st, sl.ev_done, 0));
+  h->ev_emb_hook = sl.ev_emb;
+  const int rc_enc = samroad_encode_masks(h, base, rgb_dtype, B, mask_scores_host ? sl.scores : nullptr,
+                                          nullptr, sl.emb, st);
+  h->ev_emb_hook = nullptr;
   if (rc_enc != 0) return rc_enc;
-  if (image_embeddings_host) {
-    SRB_CUDA_OK(cudaStreamWaitEvent(sc, h->ev_emb, 0));
-    SRB_CUDA_OK(cudaMemcpyAsync(image_embeddings_host, h->stage_emb, em_bytes, cudaMemcpyDeviceToHost, sc));
+  if (image_embeddings_host) {      // the embeddings go back while the mask decoder runs
+    SRB_CUDA_OK(cudaStreamWaitEvent(sc, sl.ev_emb, 0));
+    SRB_CUDA_OK(cudaMemcpyAsync(image_embeddings_host, sl.emb, em_bytes, cudaMemcpyDeviceToHost, sc));
   }
-  if (mask_scores_host) {
-    SRB_CUDA_OK(cudaEventRecord(h->ev_scores, st));
-    SRB_CUDA_OK(cudaStreamWaitEvent(sc, h->ev_scores, 0));
-    SRB_CUDA_OK(cudaMemcpyAsync(mask_scores_host, h->stage_scores, sc_bytes, cudaMemcpyDeviceToHost, sc));
+  if (mask_scores_host) {           // the mask scores while TopoNet runs
+    SRB_CUDA_OK(cudaEventRecord(sl.ev_scores, st));
+    SRB_CUDA_OK(cudaStreamWaitEvent(sc, sl.ev_scores, 0));
+    SRB_CUDA_OK(cudaMemcpyAsync(mask_scores_host, sl.scores, sc_bytes, cudaMemcpyDeviceToHost, sc));
   }
-  if (topo) {
-    SRB_TRY(samroad_toponet(h, h->stage_emb, base + o_pts, pts_dtype, base + o_prs, pairs_dtype,
+  if (topo)
+    SRB_TRY(samroad_toponet(h, sl.emb, base + o_pts, pts_dtype, base + o_prs, pairs_dtype,
                             reinterpret_cast<const uint8_t*>(base + o_val), B, N, Ns, Np, nullptr,
                             reinterpret_cast<float*>(base + o_ts), st));
-    if (topo_scores_host)
-      SRB_CUDA_OK(cudaMemcpyAsync(topo_scores_host, base + o_ts, ts_bytes, cudaMemcpyDeviceToHost, st));
-  }
-  SRB_CUDA_OK(cudaStreamSynchronize(st));
-  SRB_CUDA_OK(cudaStreamSynchronize(sc));
+  SRB_CUDA_OK(cudaEventRecord(sl.ev_compute, st));
+  SRB_CUDA_OK(cudaStreamWaitEvent(sc, sl.ev_compute, 0));
+  if (topo && topo_scores_host)
+    SRB_CUDA_OK(cudaMemcpyAsync(topo_scores_host, base + o_ts, ts_bytes, cudaMemcpyDeviceToHost, sc));
+  SRB_CUDA_OK(cudaEventRecord(sl.ev_done, sc));
   return 0;
+}
+
+// Blocks until everything samroad_infer_batch_host_async queued on `slot` has landed in host memory.
+extern "C" int samroad_infer_batch_host_wait(samroad_handle_t h, int slot) {
+  SRB_TRY(check_handle(h, true));
+  SRB_REQUIRE(slot == 0 || slot == 1, "samroad_infer_batch_host_wait: slot %d (want 0 or 1)", slot);
+  if (h->slots[slot].ev_done) SRB_CUDA_OK(cudaEventSynchronize(h->slots[slot].ev_done));
+  return 0;
+}
+
+// The synchronous form: one batch on slot 0, results in host memory on return.
+extern "C" int samroad_infer_batch_host(samroad_handle_t h, const void* rgb_host, int rgb_dtype,
+                                        int B, const void* points_host, int pts_dtype,
+                                        const void* pairs_host, int pairs_dtype,
+                                        const uint8_t* valid_host, int N, int Ns, int Np,
+                                        float* mask_scores_host, float* image_embeddings_host,
+                                        float* topo_scores_host) {
+  SRB_TRY(samroad_infer_batch_host_async(h, 0, rgb_host, rgb_dtype, B, points_host, pts_dtype, pairs_host,
+                                         pairs_dtype, valid_host, N, Ns, Np, mask_scores_host,
+                                         image_embeddings_host, topo_scores_host));
+  return samroad_infer_batch_host_wait(h, 0);
 }
 
 extern "C" uint64_t samroad_launch_count(int reset) { return launch_count(reset != 0); }
@@ -1093,6 +1114,7 @@ extern "C" int samroad_op_attention(const void* qkv16, const float* qkv_bias, co
                            static_cast<cudaStream_t>(stream));
 }
 extern "C" void samroad_debug_force_simt_attention(int on) { attention_force_simt(on); }
+extern "C" void samroad_debug_set_traverse_reverse(int on) { set_traverse_reverse(on != 0); }
 extern "C" void samroad_debug_attention_trace(void* dev_buf) { attention_set_trace(static_cast<long long*>(dev_buf)); }
 extern "C" void samroad_debug_disable_2cta_gemm(int off) {
   gemm_disable_2cta(off);

@@ -278,3 +278,39 @@ def test_attention_tc_vs_simt(B, s, win, heads, hd):
     assert torch.isfinite(outs[1]).all()
     # P is rounded to fp16 (rel 2^-11) before the PV MMA and the output to fp16: a few output ulps
     assert err <= 2.5e-3 * mag and mean_err <= 2e-4 * mag, (err, mean_err, mag)
+
+
+@pytest.mark.parametrize("B,s,win,heads,hd", [(64, 16, 14, 12, 64), (48, 32, 14, 12, 64), (64, 16, 16, 12, 64),
+                                              (64, 16, 14, 16, 80)])
+def test_attention_run_to_run_determinism(B, s, win, heads, hd):
+    """The same QKV through the tcgen05 attention twelve times per unit order (ascending / descending,
+    `set_traverse_reverse`) must give identical bits, on inputs that were just rewritten (L2-resident)
+    -- every CTA runs ~20 units back to back, window units with idle softmax warps included.
+    Regression test of a schedule-dependent corruption (rel-pos gather scratch shared across warps)."""
+    lib = _lib.load()
+    D = heads * hd
+    g = torch.Generator().manual_seed(5)
+    qkv16 = (torch.randn(B * s * s, 3 * D, generator=g) * 1.5).to(torch.float16).to(DEV)
+    bias = (0.5 * torch.randn(3 * D, generator=g)).to(torch.float16).float().to(DEV)
+    rel_h = (0.3 * torch.randn(2 * win - 1, hd, generator=g)).to(DEV)
+    rel_w = (0.3 * torch.randn(2 * win - 1, hd, generator=g)).to(DEV)
+    try:
+        for rev in (0, 1):
+            first = None
+            for it in range(12):
+                out = torch.full((B * s * s, D), float("nan"), dtype=torch.float16, device=DEV)
+                qkv16.copy_(qkv16.clone())
+                lib.samroad_debug_set_traverse_reverse(rev)
+                _lib.check(lib.samroad_op_attention(qkv16.data_ptr(), bias.data_ptr(), rel_h.data_ptr(),
+                                                    rel_w.data_ptr(), B, s, win, heads, hd, out.data_ptr(),
+                                                    _st()), "attention")
+                if first is None:
+                    first = out
+                else:
+                    assert torch.equal(first, out), (rev, it, int((first != out).sum()))
+            assert torch.isfinite(first.float()).all()
+            if rev == 0:
+                fwd = first
+        assert torch.equal(fwd, first)        # unit order must not change any bit either
+    finally:
+        lib.samroad_debug_set_traverse_reverse(0)
