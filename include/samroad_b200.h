@@ -136,8 +136,9 @@ typedef int (*samroad_argsort_fn)(const void* keys, int key_dtype, int64_t n, in
  * scores > 1.0 never suppressed).  keypoint_mask / road_mask: device uint8 [H,W] (the fused masks of
  * inferencer.py:106-110); thresholds are config.*_THRESHOLD * 255 (compared as `mask > thr`).
  * Output: device int64 [n,2] (x,y) in the reference's order, *n_points on the host.  stats (host,
- * optional, 8 ints): candidates of the two masks, survivors of passes 1-2, NMS rounds of the three
- * passes, n.  Synchronises the stream. */
+ * optional, 16 ints): candidates of the two masks, survivors of passes 1-2, NMS rounds of the three
+ * passes, n; then microseconds of host wall clock: candidates, ordering of the three passes, NMS of the
+ * three passes, total.  Synchronises the stream. */
 int samroad_extract_graph_points(samroad_graph_t g, const uint8_t* keypoint_mask,
                                  const uint8_t* road_mask, int H, int W, double itsc_thr255,
                                  double road_thr255, double itsc_radius, double road_radius,

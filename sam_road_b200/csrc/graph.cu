@@ -23,6 +23,7 @@
 
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstdio>
@@ -658,6 +659,12 @@ extern "C" int samroad_extract_graph_points(samroad_graph_t g, const uint8_t* ke
   const double thr[2] = {itsc_thr255, road_thr255};
   const double radius[2] = {itsc_radius, road_radius};
   int n_cand[2] = {0, 0}, n_kept[2] = {0, 0}, rounds[3] = {0, 0, 0};
+  using clk = std::chrono::steady_clock;
+  auto us_since = [](clk::time_point t) {
+    return static_cast<int32_t>(std::chrono::duration_cast<std::chrono::microseconds>(clk::now() - t).count());
+  };
+  const clk::time_point t_begin = clk::now();
+  int32_t us_cand = 0, us_order[3] = {0, 0, 0}, us_nms[3] = {0, 0, 0};
 
   // candidates of both masks (np.where order).  Worst case every pixel qualifies.
   for (int m = 0; m < 2; ++m) {
@@ -667,6 +674,7 @@ extern "C" int samroad_extract_graph_points(samroad_graph_t g, const uint8_t* ke
     if (int rc = compact(g, mc, npx, tot + m, st)) return rc;
   }
   if (int rc = read_ints(g, tot, 2, n_cand, st)) return rc;
+  us_cand = us_since(t_begin);
 
   // passes 1 and 2: per-mask NMS (graph_extraction.py:131-134)
   for (int m = 0; m < 2; ++m) {
@@ -676,6 +684,7 @@ extern "C" int samroad_extract_graph_points(samroad_graph_t g, const uint8_t* ke
     if (int rc = g->order.ensure(sizeof(int32_t) * static_cast<size_t>(n))) return rc;
     if (int rc = g->sorted_pix.ensure(sizeof(int32_t) * static_cast<size_t>(n))) return rc;
     if (int rc = g->immune.ensure(static_cast<size_t>(n))) return rc;
+    clk::time_point t0 = clk::now();
     if (int rc = make_order_u8(g, g->cand_score[m].as<uint8_t>(), n, argsort, user, g->order.as<int32_t>(),
                                tot + 4, st))
       return rc;
@@ -687,9 +696,12 @@ extern "C" int samroad_extract_graph_points(samroad_graph_t g, const uint8_t* ke
     int info[2];
     if (int rc = read_ints(g, tot + 4, 2, info, st)) return rc;
     SRB_REQUIRE(info[0] == 0, "argsort callback returned an invalid permutation (code %d) for mask %d", info[0], m);
+    us_order[m] = us_since(t0);
+    t0 = clk::now();
     if (int rc = nms_pass(g, g->sorted_pix.as<int32_t>(), g->immune.as<uint8_t>(), n, info[1], H, W, radius[m],
                           g->list[m].as<int32_t>(), &n_kept[m], &rounds[m], st))
       return rc;
+    us_nms[m] = us_since(t0);
   }
 
   // pass 3: intersections first (graph_extraction.py:135-138), radius = ROAD_NMS_RADIUS
@@ -700,6 +712,7 @@ extern "C" int samroad_extract_graph_points(samroad_graph_t g, const uint8_t* ke
     if (int rc = g->order.ensure(sizeof(int32_t) * static_cast<size_t>(n3))) return rc;
     if (int rc = g->sorted_pix.ensure(sizeof(int32_t) * static_cast<size_t>(n3))) return rc;
     if (int rc = g->flags32.ensure(sizeof(int32_t) * static_cast<size_t>(n3))) return rc;
+    clk::time_point t0 = clk::now();
     concat_kernel<<<blocks_for(n3), 256, 0, st>>>(g->list[0].as<int32_t>(), m0, g->list[1].as<int32_t>(), m1,
                                                   g->cand3.as<int32_t>());
     note_launch();
@@ -725,9 +738,12 @@ extern "C" int samroad_extract_graph_points(samroad_graph_t g, const uint8_t* ke
     int err = 0;
     if (int rc = read_ints(g, tot + 4, 1, &err, st)) return rc;
     SRB_REQUIRE(err == 0, "argsort callback returned an invalid permutation (code %d) for the merged pass", err);
+    us_order[2] = us_since(t0);
+    t0 = clk::now();
     if (int rc = nms_pass(g, g->sorted_pix.as<int32_t>(), nullptr, n3, n3, H, W, road_radius,
                           g->flags32.as<int32_t>(), &n_out, &rounds[2], st))
       return rc;
+    us_nms[2] = us_since(t0);
     SRB_REQUIRE(points_xy != nullptr || n_out == 0, "samroad_extract_graph_points: null output");
     SRB_REQUIRE(n_out <= cap, "samroad_extract_graph_points: %d keypoints exceed the output capacity %d", n_out, cap);
     if (n_out > 0) {
@@ -740,6 +756,9 @@ extern "C" int samroad_extract_graph_points(samroad_graph_t g, const uint8_t* ke
   if (stats) {
     stats[0] = n_cand[0]; stats[1] = n_cand[1]; stats[2] = m0; stats[3] = m1;
     stats[4] = rounds[0]; stats[5] = rounds[1]; stats[6] = rounds[2]; stats[7] = n_out;
+    // host wall-clock split in microseconds (each stage ends on a stream synchronisation)
+    stats[8] = us_cand; stats[9] = us_order[0]; stats[10] = us_order[1]; stats[11] = us_order[2];
+    stats[12] = us_nms[0]; stats[13] = us_nms[1]; stats[14] = us_nms[2]; stats[15] = us_since(t_begin);
   }
   return 0;
 }

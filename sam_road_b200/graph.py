@@ -95,7 +95,7 @@ class SceneGraph:
         if self._points_buf is None or self._points_buf.shape[0] < cap:
             self._points_buf = torch.empty((cap, 2), dtype=torch.int64, device=self.device)
         n = C.c_int(0)
-        stats = (C.c_int32 * 8)()
+        stats = (C.c_int32 * 16)()
         cb = _NUMPY_ARGSORT_CB if tie_order == "numpy" else _NULL_CB
         with torch.cuda.device(self.device):
             _lib.check(_lib.load().samroad_extract_graph_points(
@@ -104,7 +104,9 @@ class SceneGraph:
                 float(road_nms_radius), cb, None, self._points_buf.data_ptr(), cap, C.byref(n), stats,
                 _lib.current_stream_ptr()), "samroad_extract_graph_points")
         self.stats.update(candidates=(stats[0], stats[1]), pass_survivors=(stats[2], stats[3]),
-                          nms_rounds=(stats[4], stats[5], stats[6]), n_points=n.value, tie_order=tie_order)
+                          nms_rounds=(stats[4], stats[5], stats[6]), n_points=n.value, tie_order=tie_order,
+                          us=dict(candidates=stats[8], order=(stats[9], stats[10], stats[11]),
+                                  nms=(stats[12], stats[13], stats[14]), total=stats[15]))
         return self._points_buf[: n.value].clone()
 
     # ---- pair queries -------------------------------------------------------------------------------

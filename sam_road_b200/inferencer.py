@@ -180,7 +180,12 @@ def infer_one_img(net, img: np.ndarray, config, device: Optional[torch.device] =
     # ---- pass 2: TopoNet on the stored features -------------------------------------------------------
     K = int(_cfg_get(config, "MAX_NEIGHBOR_QUERIES"))
     R = float(_cfg_get(config, "NEIGHBOR_RADIUS"))
+    def _mark():
+        if timings is not None:
+            torch.cuda.synchronize(device)
+        return time.perf_counter()
     counts = gx.plan_pair_queries(points_d, tile_xy, P, R)
+    t_plan = _mark()
     # layout of the scene-wide score buffer: per batch [n, nmax_of_the_batch, K] (inferencer.py:179-185
     # pads every batch to its own maximum); batches with no point at all are skipped (188-189)
     plan = batch_plan(n_tiles, bs, world)
@@ -204,7 +209,9 @@ def infer_one_img(net, img: np.ndarray, config, device: Optional[torch.device] =
             out.copy_(net.infer_toponet(feats[b0 - lo: b0 - lo + nb], pts, prs, val).reshape(-1))
     if world > 1:   # every element is written by exactly one rank (zeros elsewhere): the sum is exact
         dist.all_reduce(topo_flat, op=dist.ReduceOp.SUM, group=group)
+    t_topo = _mark()
     edges_d = gx.aggregate_edges(topo_flat, tile_off, K, float(_cfg_get(config, "TOPO_THRESHOLD")))
+    t_agg = _mark()
     graph_points = points_d.cpu().numpy()
     pred_edges = edges_d.cpu().numpy()
     if pred_edges.shape[0] == 0:
@@ -214,8 +221,10 @@ def infer_one_img(net, img: np.ndarray, config, device: Optional[torch.device] =
     if timings is not None:
         t_end = time.perf_counter()
         timings.update(pass1_s=t_pass1 - t_start, keypoints_s=t_points - t_pass1,
-                       pass2_s=t_end - t_points, total_s=t_end - t_start, n_tiles=n_tiles,
-                       n_points=n_points, n_edges=int(pred_edges.shape[0]), graph_stats=dict(gx.stats),
+                       pass2_s=t_end - t_points, pair_queries_s=t_plan - t_points, toponet_s=t_topo - t_plan,
+                       edges_s=t_agg - t_topo, download_s=t_end - t_agg, total_s=t_end - t_start,
+                       n_tiles=n_tiles, n_points=n_points, n_edges=int(pred_edges.shape[0]),
+                       graph_stats=dict(gx.stats),
                        topo_samples=int(sum(nb * nm for (_, _, nb), nm in zip(plan, batch_nmax))))
     return pred_nodes, pred_edges, kp_h.numpy().copy(), road_h.numpy().copy()
 
