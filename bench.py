@@ -343,8 +343,8 @@ def run_native(args, w, wl):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # the all-gathers run beside the next step's compute: keep NCCL's footprint on the SMs small
-        os.environ.setdefault("NCCL_MAX_CTAS", "8")
+        from sam_road_b200.exchange import limit_nccl_ctas
+        limit_nccl_ctas(world)          # only matters on the NCCL fallback of the exchange (sam_road_b200/exchange.py)
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     CONFIG = w["cfg"]
@@ -362,34 +362,39 @@ def run_native(args, w, wl):
     topo_host = [synth.make_topo_inputs(B, P, NP, seed=100 * rank + r, ragged=False) for r in range(R)] if NP else None
     topo = [[t.to(dev) for t in th] for th in topo_host] if NP else None
 
-    # exchange step of the path: per-tile mask scores and topology scores to every rank.
-    # Double-buffered and issued asynchronously: step i's all-gathers run under step i+1's compute.
-    gather_sc = gather_ts = None
-    pending = []
+    # exchange step of the path: per-tile mask scores and topology scores to every rank,
+    # double-buffered and asynchronous -- step i's exchange runs under step i+1's compute, on the copy
+    # engines over NVLink peer memory when symmetric memory is available (sam_road_b200/exchange.py).
+    ex_sc = ex_ts = None
     if world > 1:
-        gather_sc = [torch.empty((world * B, P, P, 2), dtype=torch.float32, device=dev) for _ in range(2)]
+        from sam_road_b200.exchange import TileExchange
+        ex_sc = TileExchange(B, (P, P, 2), torch.float32, dev, slots=2, prefer_copy_engine=not args.nccl_exchange)
         if NP:
-            gather_ts = [torch.empty((world * B, NP, 16, 1), dtype=torch.float32, device=dev) for _ in range(2)]
+            ex_ts = TileExchange(B, (NP, 16, 1), torch.float32, dev, slots=2, prefer_copy_engine=not args.nccl_exchange)
     _mem_line("native arm, inputs resident", dev)
 
     def step(i):
-        r = i % R
+        r, sl = i % R, i % 2
+        if world > 1:      # results are produced straight into this rank's block of the gather buffer
+            ex_sc.wait(sl)
+            scores, feat = net._encode(tiles[r], False, out_scores=ex_sc.local_block(sl))[::2]
+            ts = None
+            if NP:
+                ex_ts.wait(sl)
+                ts = net.infer_toponet(feat, *topo[r], out=ex_ts.local_block(sl))
+            ex_sc.publish(sl)
+            if NP:
+                ex_ts.publish(sl)
+            return scores, ts
         scores, feat = net.infer_masks_and_img_features(tiles[r])
         ts = net.infer_toponet(feat, *topo[r]) if NP else None
-        if world > 1:
-            while len(pending) >= 2:                       # buffer (i % 2) is free once step i-2's gathers are done
-                for wk in pending.pop(0)[0]:
-                    wk.wait()
-            works = [dist.all_gather_into_tensor(gather_sc[i % 2], scores, async_op=True)]
-            if NP:
-                works.append(dist.all_gather_into_tensor(gather_ts[i % 2], ts, async_op=True))
-            pending.append((works, scores, ts))            # keep the sources alive until the collective has read them
         return scores, ts
 
     def drain():
-        while pending:
-            for wk in pending.pop(0)[0]:
-                wk.wait()
+        if world > 1:
+            ex_sc.drain()
+            if NP:
+                ex_ts.drain()
 
     def barrier():
         drain()
@@ -430,7 +435,8 @@ def run_native(args, w, wl):
     h_tiles = [t.cpu().pin_memory() for t in tiles]
     h_topo = [[t.contiguous().pin_memory() for t in (th[0], th[1], th[2].view(torch.uint8))]
               for th in topo_host] if NP else None
-    del tiles, topo, gather_sc, gather_ts               # the e2e leg owns its own (staged) device buffers
+    exchange_backend = (ex_sc.backend + (f" ({ex_sc.note})" if ex_sc.note else "")) if ex_sc is not None else None
+    del tiles, topo, ex_sc, ex_ts                        # the e2e leg owns its own (staged) device buffers
     torch.cuda.empty_cache()
     h_scores = [torch.empty((B, P, P, 2), dtype=torch.float32).pin_memory() for _ in range(2)]
     h_emb = [torch.empty((B, 256, P // 16, P // 16), dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -523,8 +529,9 @@ def run_native(args, w, wl):
                    "l2_policy": f"{R} rotating resident input batches and >1 GB of activations per step "
                                 "(> 126 MB L2); no explicit flush",
                    "parallelism": f"tile-sharded dp{world}" +
-                                  (" + async all_gather(mask scores, topo scores) overlapped with the next step"
-                                   if world > 1 else "")},
+                                  (" + all-gather of mask scores and topology scores, double-buffered, overlapped with "
+                                   "the next step" if world > 1 else ""),
+                   "exchange": exchange_backend},
         "e2e": {"value": e2e_value, "unit": "tiles/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps,
                 "call": "samroad_infer_batch_host_async / _wait, two staging slots (pinned host uint8 tiles -> mask "
@@ -563,8 +570,9 @@ class _JsonStdout:
         os.write(self.fd, (line + "\n").encode())
 
     def __exit__(self, *a):
+        # fd 1 stays pointed at stderr for the rest of the process: NCCL (NCCL_DEBUG=INFO) still prints
+        # while the communicator is torn down at interpreter exit
         sys.stdout.flush()
-        os.dup2(self.fd, 1)
         os.close(self.fd)
 
 
@@ -592,6 +600,8 @@ def main():
                     help="tiles per step of the CPU reference arm (bounded sample)")
     ap.add_argument("--scene-runs", type=int, default=5, help="timed infer_one_img runs per scene and tie order")
     ap.add_argument("--no-scene", action="store_true", help="skip the e2e_scene legs")
+    ap.add_argument("--nccl-exchange", action="store_true",
+                    help="A/B: force the NCCL all-gather fallback of the exchange step (default: copy engines)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--debug-gemm-mode", type=int, default=0,
                     help="A/B only: samroad_debug_disable_2cta_gemm bit mask (16 = no snake traversal)")

@@ -15,9 +15,10 @@ on the GPU:
     are device kernels behind `sam_road_b200.graph.SceneGraph` (csrc/graph.cu): exact greedy NMS in the
     reference's visiting order, exact kNN, float32 sums in the reference's (tile, sample, pair) order;
   * with torch.distributed initialised, tiles are sharded over ranks in contiguous blocks, the
-    per-tile mask scores are exchanged with ONE all-gather, the topology scores with one all-reduce of
-    a disjointly-written buffer, and every rank fuses / aggregates in global tile order -> identical
-    masks and graph on all ranks and at any world size.
+    per-tile mask scores are all-gathered once (by the copy engines over NVLink peer memory, batch by
+    batch under the next batch's compute: sam_road_b200/exchange.py), the topology scores with one
+    all-reduce of a disjointly-written buffer, and every rank fuses / aggregates in global tile order
+    -> identical masks and graph on all ranks and at any world size.
 There is no CPU path: without the CUDA library every stage raises.
 """
 from __future__ import annotations
@@ -78,6 +79,17 @@ def fuse_masks_device(scores: torch.Tensor, tiles: Sequence[TileInfo], H: int, W
 
 
 _GRAPHS: Dict[int, SceneGraph] = {}
+_EXCHANGES: Dict[tuple, "object"] = {}
+
+
+def _exchange(rows_per_rank: int, P: int, device: torch.device, group, world: int):
+    """Cached gather buffers of the mask-score exchange (allocating symmetric memory is a collective)."""
+    from .exchange import TileExchange
+    key = (rows_per_rank, P, device.index, id(group), world)
+    if key not in _EXCHANGES:
+        _EXCHANGES.clear()
+        _EXCHANGES[key] = TileExchange(rows_per_rank, (P, P, 2), torch.float32, device, group=group, slots=1)
+    return _EXCHANGES[key]
 _PINNED: Dict[Tuple[int, int], Tuple[torch.Tensor, torch.Tensor]] = {}
 
 
@@ -131,11 +143,18 @@ def infer_one_img(net, img: np.ndarray, config, device: Optional[torch.device] =
 
     # ---- pass 1: masks + image features of the tiles this rank owns -------------------------------
     img_d = torch.as_tensor(np.ascontiguousarray(img)).to(device)               # one H2D of the scene
-    scores_all = torch.empty((per * world, P, P, 2), dtype=torch.float32, device=device)
-    my_scores = scores_all[rank * per: rank * per + per]
+    ex = None
+    if world > 1:   # the exchange step: every rank's per-tile mask scores to every rank
+        ex = _exchange(per, P, device, group, world)
+        ex.wait(0)
+        scores_all, my_scores = ex.gathered(0), ex.local_block(0)
+    else:
+        scores_all = torch.empty((per, P, P, 2), dtype=torch.float32, device=device)
+        my_scores = scores_all
     feats = torch.empty((max(n_mine, 1), 256, s, s), dtype=torch.float32, device=device)
     scene_call = getattr(net, "infer_masks_and_img_features_scene", None)
-    for b0 in range(0, n_mine, bs):
+    n_batches = (n_mine + bs - 1) // bs
+    for bi, b0 in enumerate(range(0, n_mine, bs)):
         nb = min(bs, n_mine - b0)
         if scene_call is not None:
             scene_call(img_d, tile_xy[lo + b0: lo + b0 + nb], out_scores=my_scores[b0:b0 + nb],
@@ -145,10 +164,12 @@ def infer_one_img(net, img: np.ndarray, config, device: Optional[torch.device] =
             sc, ft = net.infer_masks_and_img_features(rgb)
             my_scores[b0:b0 + nb].copy_(sc)
             feats[b0:b0 + nb].copy_(ft)
-    if world > 1:   # the exchange step: one all-gather of per-tile mask scores
-        if n_mine < per:
-            my_scores[n_mine:].zero_()
-        dist.all_gather_into_tensor(scores_all, my_scores.clone(), group=group)
+        if ex is not None:      # a batch's scores leave while the next batch computes
+            ex.publish(0, b0, b0 + nb, first=bi == 0, last=bi == n_batches - 1)
+    if ex is not None:
+        if n_batches == 0:      # more ranks than tiles: still part of the round
+            ex.publish(0, 0, 0, first=True, last=True)
+        ex.wait(0)
     kp_d, road_d = fuse_masks_device(scores_all[:n_tiles], tiles, H, W)
     # the masks are return values: start their download now, it overlaps the graph stage
     kp_h, road_h = _pinned_masks(H, W)
