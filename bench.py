@@ -300,7 +300,8 @@ def run_scenes(args, w, wl, dev, rank, world, barrier):
                "h2d_bytes_per_scene": int(img.nbytes)}
         for tie in ("numpy", "stable"):
             tm = {}
-            infer_one_img(net, img, cfg, device=dev, nms_tie_order=tie, timings=tm)      # warm-up + stage split
+            infer_one_img(net, img, cfg, device=dev, nms_tie_order=tie)                  # warm-up
+            infer_one_img(net, img, cfg, device=dev, nms_tie_order=tie, timings=tm)      # stage split (with syncs)
             times = []
             for _ in range(args.scene_runs):
                 barrier()
@@ -382,19 +383,19 @@ def run_native(args, w, wl):
             if NP:
                 ex_ts.wait(sl)
                 ts = net.infer_toponet(feat, *topo[r], out=ex_ts.local_block(sl))
-            ex_sc.publish(sl)
-            if NP:
-                ex_ts.publish(sl)
+            if not args.no_exchange:
+                ex_sc.publish(sl)
+                if NP:
+                    ex_ts.publish(sl)
             return scores, ts
         scores, feat = net.infer_masks_and_img_features(tiles[r])
         ts = net.infer_toponet(feat, *topo[r]) if NP else None
         return scores, ts
 
     def drain():
-        if world > 1:
-            ex_sc.drain()
-            if NP:
-                ex_ts.drain()
+        for ex in (ex_sc, ex_ts):
+            if ex is not None:
+                ex.drain()
 
     def barrier():
         drain()
@@ -425,10 +426,12 @@ def run_native(args, w, wl):
     _lib.check(lib.samroad_timing_read(handle, buf, len(buf)), "timing_read")
     kernels = json.loads(buf.value.decode())
     _lib.check(lib.samroad_timing_enable(handle, 0), "timing_disable")
+    ms_ranks = [ms]
     if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = t.item()
+        allms = [torch.zeros(1, device=dev) for _ in range(world)]
+        dist.all_gather(allms, torch.tensor([ms], device=dev))
+        ms_ranks = [float(x.item()) for x in allms]
+        ms = max(ms_ranks)               # the slowest rank decides
     value = world * B * args.steps / (ms / 1e3)
 
     # ---- e2e: the host-buffer C-ABI call, pinned host tiles in, results out, every step ----------
@@ -436,7 +439,8 @@ def run_native(args, w, wl):
     h_topo = [[t.contiguous().pin_memory() for t in (th[0], th[1], th[2].view(torch.uint8))]
               for th in topo_host] if NP else None
     exchange_backend = (ex_sc.backend + (f" ({ex_sc.note})" if ex_sc.note else "")) if ex_sc is not None else None
-    del tiles, topo, ex_sc, ex_ts                        # the e2e leg owns its own (staged) device buffers
+    del tiles, topo                                      # the e2e leg owns its own (staged) device buffers
+    ex_sc = ex_ts = None
     torch.cuda.empty_cache()
     h_scores = [torch.empty((B, P, P, 2), dtype=torch.float32).pin_memory() for _ in range(2)]
     h_emb = [torch.empty((B, 256, P // 16, P // 16), dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -521,7 +525,8 @@ def run_native(args, w, wl):
 
     line = {
         "metric": w["metric"], "value": value, "unit": "tiles/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "ms_per_step_by_rank": [round(x / args.steps, 4) for x in ms_ranks], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate",
         "data": "synthetic",
         "config": {"workload": w["name"], "workload_key": wl, "what": w["note"], "tiles_per_step_per_gpu": B,
@@ -531,7 +536,7 @@ def run_native(args, w, wl):
                    "parallelism": f"tile-sharded dp{world}" +
                                   (" + all-gather of mask scores and topology scores, double-buffered, overlapped with "
                                    "the next step" if world > 1 else ""),
-                   "exchange": exchange_backend},
+                   "exchange": "SKIPPED (--no-exchange, A/B only)" if args.no_exchange else exchange_backend},
         "e2e": {"value": e2e_value, "unit": "tiles/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps,
                 "call": "samroad_infer_batch_host_async / _wait, two staging slots (pinned host uint8 tiles -> mask "
@@ -600,6 +605,8 @@ def main():
                     help="tiles per step of the CPU reference arm (bounded sample)")
     ap.add_argument("--scene-runs", type=int, default=5, help="timed infer_one_img runs per scene and tie order")
     ap.add_argument("--no-scene", action="store_true", help="skip the e2e_scene legs")
+    ap.add_argument("--no-exchange", action="store_true",
+                    help="A/B only: skip the exchange step at N > 1 (attributes a slow step to the slowest GPU or to the exchange)")
     ap.add_argument("--nccl-exchange", action="store_true",
                     help="A/B: force the NCCL all-gather fallback of the exchange step (default: copy engines)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -254,14 +254,15 @@ static int launch_attention_tc(const __half* qkv, const float* qkv_bias, const _
       return rc;
   }
   const int rows = rel_table_rows(WIN);
+  static_assert(atc_table_rows(WIN) == (4 * WIN - 2 <= 64 ? 64 : (4 * WIN - 2 <= 128 ? 128 : 256)), "table rows");
   if (int rc = make_tmap_f16_2d(&tmTab, tab, rows, 64, 64, rows)) return rc;
   auto kern = g_poly ? attention_tc_kernel<kWindow, WIN, true> : attention_tc_kernel<kWindow, WIN, false>;
   static uint64_t attr_devs = 0;          // one bit per CUDA device: function attributes are per device
   if (first_use_on_device(&attr_devs)) {
     SRB_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<kWindow, WIN, false>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, AtcSmem<kWindow>::kBytes));
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, AtcSmem<kWindow, atc_table_bytes(WIN)>::kBytes));
     SRB_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<kWindow, WIN, true>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, AtcSmem<kWindow>::kBytes));
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, AtcSmem<kWindow, atc_table_bytes(WIN)>::kBytes));
   }
   AtcParams p;
   p.qkv_bias = qkv_bias; p.out = out; p.B = B; p.s = s; p.heads = heads; p.D = D;
@@ -274,7 +275,7 @@ static int launch_attention_tc(const __half* qkv, const float* qkv_bias, const _
   p.alternate = g_alternate ? 1 : 0;
   p.reverse = traverse_reverse() ? 1 : 0;
   const int grid = units < device_sm_count() ? units : device_sm_count();   // persistent CTAs
-  kern<<<grid, kAtcThreads, AtcSmem<kWindow>::kBytes, st>>>(tmQKV, tmTab, p);
+  kern<<<grid, kAtcThreads, AtcSmem<kWindow, atc_table_bytes(WIN)>::kBytes, st>>>(tmQKV, tmTab, p);
   SRB_CUDA_OK(cudaGetLastError());
   note_launch();
   return 0;
@@ -324,7 +325,7 @@ int encoder_attention(const __half* qkv, const float* qkv_bias, const float* rel
   if (B <= 0) return 0;
   // tensor-core path: head_dim 64; window 14 on any grid, global on 16x16 / 32x32 token grids
   const bool tc_ok = hd == 64 && !g_force_simt &&
-                     ((win == 14 && s > 14) || (win == s && (s == 16 || s == 32)));
+                     ((win == 14 && s > 14) || (win == s && (s == 16 || s == 32 || s == 64)));
   if (tc_ok) {
     const __half* tab = rel_tab;
     if (!tab) {
@@ -333,12 +334,13 @@ int encoder_attention(const __half* qkv, const float* qkv_bias, const float* rel
       SRB_CUDA_OK(cudaGetDevice(&dev));
       SRB_REQUIRE(dev >= 0 && dev < 64, "attention: device index %d", dev);
       __half*& scratch = scratch_dev[dev];
-      if (!scratch) SRB_CUDA_OK(cudaMalloc(&scratch, 128 * 64 * sizeof(__half)));
+      if (!scratch) SRB_CUDA_OK(cudaMalloc(&scratch, 256 * 64 * sizeof(__half)));
       SRB_TRY_RC(pack_rel_table(rel_h, rel_w, win, hd, scratch, st));
       tab = scratch;
     }
     if (win == 14 && win < s) return launch_attention_tc<true, 14>(qkv, qkv_bias, tab, B, s, heads, out, st);
     if (s == 16) return launch_attention_tc<false, 16>(qkv, qkv_bias, tab, B, s, heads, out, st);
+    if (s == 64) return launch_attention_tc<false, 64>(qkv, qkv_bias, tab, B, s, heads, out, st);
     return launch_attention_tc<false, 32>(qkv, qkv_bias, tab, B, s, heads, out, st);
   }
   // head_dim 80 (ViT-H): tensor-core kernel with two K-blocks per operand tile

@@ -47,13 +47,13 @@ constexpr int kAtcThreads = 384;
 // shared memory map (bytes from a 1024-aligned base)
 //   global: Q 32 KB | Tab 16 KB | K/V ring 3 x (16 K + 16 K) | P 64 KB
 //   window: Q 32 KB | Tab 16 KB | K/V 2 x (K 208 rows + V 208 rows) double-buffered across units | P 64 KB
-template <bool kWindow>
+template <bool kWindow, int kTabBytes = 16384>
 struct AtcSmem {
   static constexpr int kQStages = 1;
   static constexpr int kKVStages = kWindow ? 2 : 3;
   static constexpr int kOffQ = 0;
   static constexpr int kOffTab = kQStages * 32768;
-  static constexpr int kOffKV = kOffTab + 16384;
+  static constexpr int kOffKV = kOffTab + kTabBytes;      // 16 KB table (<= 128 rows) or 32 KB (256 rows, 64x64 grid)
   static constexpr int kKVHalf = kWindow ? 208 * 128 : 16384;     // bytes of the K (or V) part of a stage
   static constexpr int kKVStage = 2 * kKVHalf;
   static constexpr int kOffP = kOffKV + kKVStages * kKVStage;   // 2 groups x 2 k-blocks x 16 KB
@@ -77,6 +77,12 @@ struct AtcParams {
 struct AtcUnit {
   int b, head, wy, wx, slab;
 };
+
+// rows of the packed rel-pos table [rel_pos_h ; rel_pos_w]: each half must hold 2*WIN-1 rows
+__host__ __device__ constexpr int atc_table_rows(int win) {
+  return 4 * win - 2 <= 64 ? 64 : (4 * win - 2 <= 128 ? 128 : 256);
+}
+__host__ __device__ constexpr int atc_table_bytes(int win) { return atc_table_rows(win) == 256 ? 32768 : 16384; }
 
 template <bool kWindow, int WIN>
 __device__ __forceinline__ AtcUnit atc_decode(int u, const AtcParams& p) {
@@ -112,8 +118,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
                     AtcParams p) {
   constexpr int KEYS = WIN * WIN;
   constexpr int NBLK = (KEYS + 127) / 128;
-  constexpr int NTAB = (4 * WIN - 2 <= 64) ? 64 : 128;
+  constexpr int NTAB = atc_table_rows(WIN);
   constexpr int HALF = NTAB / 2;
+  // 64x64 token grid: the table has 2 x 127 rows, so the projection T = Q Tab^T is 256 columns wide.  It goes
+  // through the group's 128-column S region in two phases (rel_pos_h half, then rel_pos_w half).
+  constexpr bool kTwoPhaseT = NTAB == 256;
   constexpr int kLastKeys = KEYS - 128 * (NBLK - 1);            // real keys in the last block
   constexpr int kLastMma = ((kLastKeys + 15) / 16) * 16;        // keys the last UMMA covers
   static_assert(2 * WIN - 1 <= HALF, "rel-pos table half too small");
@@ -122,7 +131,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  using SM = AtcSmem<kWindow>;
+  using SM = AtcSmem<kWindow, atc_table_bytes(WIN)>;
   constexpr int QST = SM::kQStages;
   constexpr int kAtcKVStages = SM::kKVStages;
   constexpr int KVH = SM::kKVHalf;
@@ -244,7 +253,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       int wcnt = 0;      // writes (T or S) issued into this group's S region so far
       int tcnt = 0;      // rel-pos projections issued into this group's own T region (kSepT)
       int bcnt = 0;      // blocks completed by this group in earlier units
-      constexpr uint32_t idT = umma_idesc_f16(128, NTAB);
+      constexpr uint32_t idT = umma_idesc_f16(128, kTwoPhaseT ? 128 : NTAB);
       constexpr uint32_t idPV = umma_idesc_f16_bmn(128, 64);
       for (int u = blockIdx.x; u < p.num_units; u += gridDim.x, ++ui) {
         const AtcUnit un = atc_decode<kWindow, WIN>(u, p);
@@ -294,7 +303,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
           wcnt++;
           if (jb == NBLK - 1) umma_commit(&q_empty[qs]);   // Q tile reusable once these MMAs retire
         };
-        {   // rel-pos projection T_g = Q_g * Tab^T (own TMEM region, or the S region)
+        if constexpr (kTwoPhaseT) {
+          // T_h = Q_g * rel_pos_h^T, then (once the group has gathered it) T_w = Q_g * rel_pos_w^T, both
+          // through the S region; t_ready completes twice per unit (phases 2*ui and 2*ui+1)
+          constexpr uint32_t idT128 = umma_idesc_f16(128, 128);
+          const uint64_t adesc = umma_desc_k128(smem_u32(sQu + g * 16384));
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            wait_s_region();
+            const uint64_t bdesc = umma_desc_k128(smem_u32(sTab + half * 16384));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16_ss(tmem_base + g * 128, adesc + 2 * k, bdesc + 2 * k, idT128, k != 0 ? 1u : 0u);
+            wcnt++;
+            umma_commit(&t_ready[g]);
+          }
+        } else {   // rel-pos projection T_g = Q_g * Tab^T (own TMEM region, or the S region)
           if constexpr (kSepT) {
             if (tcnt > 0) {
               mbar_wait(&t_free[g], (tcnt - 1) & 1);
@@ -458,28 +482,43 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       // rel_h[kh] = T_h[qy - kh + WIN-1] ; rel_w[kw] = T_w[qx - kw + WIN-1]  (image_encoder.py:318-322)
       float rel_h[WIN], rel_w[WIN];
       {
-        if constexpr (!kWindow) mbar_wait(&t_ready[g], ui & 1);
+        if constexpr (!kWindow && !kTwoPhaseT) mbar_wait(&t_ready[g], ui & 1);
         tc_fence_after_sync();
         const int sy = (kWindow && qrow >= KEYS) ? 0 : qy;
         const int sx = (kWindow && qrow >= KEYS) ? 0 : qx;
+        // a half of the table (HALF candidate rows per query) goes through the thread's 64-float scratch
+        // in rounds of 64 columns; each rel_*[i] = T[sh - i] is picked up in the round that holds its column
+        constexpr int kRound = HALF < 64 ? HALF : 64;
+        constexpr int kRounds = HALF / kRound;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-#pragma unroll
-          for (int c = 0; c < HALF / 32; ++c) {
-            uint32_t r32[32];
-            tmem_ld_32x32((kSepT ? tT : tS) + half * HALF + c * 32, r32);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) *scr(c * 32 + i) = __uint_as_float(r32[i]);
+          if constexpr (kTwoPhaseT) {
+            mbar_wait(&t_ready[g], static_cast<uint32_t>(half));     // phases 2*ui + half
+            tc_fence_after_sync();
           }
-          if (half == 1) {
-            tc_fence_before_sync();
-            mbar_arrive(kSepT ? &t_free[g] : &s_free[g]);   // T consumed: the region may be overwritten
-          }
+          const uint32_t tsrc = (kSepT ? tT : tS) + (kTwoPhaseT ? 0 : half * HALF);
           const int sh = (half == 0 ? sy : sx) + WIN - 1;
 #pragma unroll
-          for (int i = 0; i < WIN; ++i) {
-            const float v = *scr(sh - i) * kLog2e;
-            if (half == 0) rel_h[i] = v; else rel_w[i] = v;
+          for (int r = 0; r < kRounds; ++r) {
+#pragma unroll
+            for (int c = 0; c < kRound / 32; ++c) {
+              uint32_t r32[32];
+              tmem_ld_32x32(tsrc + r * 64 + c * 32, r32);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) *scr(c * 32 + i) = __uint_as_float(r32[i]);
+            }
+            if (r == kRounds - 1 && (half == 1 || kTwoPhaseT)) {
+              tc_fence_before_sync();
+              mbar_arrive(kSepT ? &t_free[g] : &s_free[g]);   // T consumed: the region may be overwritten
+            }
+#pragma unroll
+            for (int i = 0; i < WIN; ++i) {
+              const int j = sh - i;
+              if (kRounds == 1 || (j >> 6) == r) {
+                const float v = *scr(j & 63) * kLog2e;
+                if (half == 0) rel_h[i] = v; else rel_w[i] = v;
+              }
+            }
           }
         }
       }

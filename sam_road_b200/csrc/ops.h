@@ -67,8 +67,8 @@ int convert_f32_f16(const float* x, long n, __half* out, cudaStream_t st);
 int encoder_attention(const __half* qkv, const float* qkv_bias, const float* rel_h,
                       const float* rel_w, const __half* rel_tab, int B, int s, int win, int heads,
                       int hd, __half* out, cudaStream_t st);
-// rows of the packed table for a window size (64 if 4*win-2 <= 64 else 128)
-inline int rel_table_rows(int win) { return 4 * win - 2 <= 64 ? 64 : 128; }
+// rows of the packed table for a window size: each half holds 2*win-1 rows (64 / 128 / 256 rows in all)
+inline int rel_table_rows(int win) { return 4 * win - 2 <= 64 ? 64 : (4 * win - 2 <= 128 ? 128 : 256); }
 int pack_rel_table(const float* rel_h, const float* rel_w, int win, int hd, __half* tab,
                    cudaStream_t st);
 // force the SIMT v1 attention kernel (tests use it as the independent on-device checker)

@@ -250,7 +250,8 @@ def test_encoder_attention(B, s, win, heads, hd):
 
 @pytest.mark.parametrize("B,s,win,heads,hd", [(3, 32, 14, 12, 64), (3, 32, 32, 12, 64), (5, 16, 14, 12, 64),
                                               (5, 16, 16, 12, 64), (12, 16, 14, 16, 80), (12, 16, 16, 16, 80),
-                                              (3, 32, 14, 16, 80), (2, 32, 32, 16, 80)])
+                                              (3, 32, 14, 16, 80), (2, 32, 32, 16, 80),
+                                              (2, 64, 64, 12, 64), (1, 64, 14, 12, 64)])   # PATCH_SIZE 1024: 64x64 grid
 def test_attention_tc_vs_simt(B, s, win, heads, hd):
     """tcgen05 kernels (head_dim 64 and 80) against the fp32 SIMT kernel on identical inputs
     (independent checker); batches large enough that every CTA runs several units."""
@@ -281,7 +282,7 @@ def test_attention_tc_vs_simt(B, s, win, heads, hd):
 
 
 @pytest.mark.parametrize("B,s,win,heads,hd", [(64, 16, 14, 12, 64), (48, 32, 14, 12, 64), (64, 16, 16, 12, 64),
-                                              (64, 16, 14, 16, 80)])
+                                              (64, 16, 14, 16, 80), (3, 64, 64, 12, 64)])
 def test_attention_run_to_run_determinism(B, s, win, heads, hd):
     """The same QKV through the tcgen05 attention twelve times per unit order (ascending / descending,
     `set_traverse_reverse`) must give identical bits, on inputs that were just rewritten (L2-resident)
