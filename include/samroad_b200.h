@@ -126,7 +126,9 @@ int samroad_graph_destroy(samroad_graph_t g);
  * Returns 0 on success.  graph_utils.nms_points visits candidates in `argsort(scores)[::-1]` order
  * (graph_utils.py:574); the order of EQUAL scores is an implementation detail of NumPy's unstable
  * sort (it differs between CPUs), so a caller that needs the reference's exact keypoints on this host
- * passes NumPy's permutation in; with NULL the device sorts as argsort(kind='stable')[::-1] would. */
+ * passes NumPy's permutation in; with NULL the device sorts as argsort(kind='stable')[::-1] would.
+ * The callback may be invoked from up to three library threads at once (the three sorts of one call
+ * are independent) and must be thread-safe. */
 typedef int (*samroad_argsort_fn)(const void* keys, int key_dtype, int64_t n, int64_t* order_out,
                                   void* user);
 

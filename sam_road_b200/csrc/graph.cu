@@ -27,6 +27,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdio>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -572,14 +573,18 @@ int nms_pass(samroad_graph_ctx* g, const int32_t* sorted_pix, const uint8_t* imm
 
 // visiting order of a uint8-scored candidate set: host permutation (NumPy) or device stable sort
 int make_order_u8(samroad_graph_ctx* g, const uint8_t* score_dev, int n, samroad_argsort_fn cb, void* user,
-                  int32_t* order, int* err_dev, cudaStream_t st) {
+                  const std::vector<int64_t>* pre_asc, int32_t* order, int* err_dev, cudaStream_t st) {
   if (n == 0) return 0;
   if (cb) {
-    std::vector<uint8_t> keys(n);
-    std::vector<int64_t> asc(n);
-    SRB_CUDA_OK(cudaMemcpyAsync(keys.data(), score_dev, n, cudaMemcpyDeviceToHost, st));
-    SRB_CUDA_OK(cudaStreamSynchronize(st));
-    SRB_REQUIRE(cb(keys.data(), SAMROAD_U8, n, asc.data(), user) == 0, "argsort callback failed (uint8 scores)");
+    std::vector<int64_t> own;
+    if (!pre_asc) {
+      std::vector<uint8_t> keys(n);
+      own.resize(n);
+      SRB_CUDA_OK(cudaMemcpyAsync(keys.data(), score_dev, n, cudaMemcpyDeviceToHost, st));
+      SRB_CUDA_OK(cudaStreamSynchronize(st));
+      SRB_REQUIRE(cb(keys.data(), SAMROAD_U8, n, own.data(), user) == 0, "argsort callback failed (uint8 scores)");
+    }
+    const std::vector<int64_t>& asc = pre_asc ? *pre_asc : own;
     if (int rc = g->ghist.ensure(sizeof(int64_t) * n)) return rc;
     SRB_CUDA_OK(cudaMemcpyAsync(g->ghist.p, asc.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice, st));
     order_from_host_kernel<<<blocks_for(n), 256, 0, st>>>(g->ghist.as<int64_t>(), n, order, err_dev);
@@ -676,6 +681,39 @@ extern "C" int samroad_extract_graph_points(samroad_graph_t g, const uint8_t* ke
   if (int rc = read_ints(g, tot, 2, n_cand, st)) return rc;
   us_cand = us_since(t_begin);
 
+  // Host permutations (NumPy tie order): when every candidate score is > 1 the first two passes only reorder,
+  // so the sizes of the third pass are known now and the three argsorts can run side by side (np.argsort
+  // releases the GIL): uint8 scores of the two masks, float64 priorities [1]*n0 + [0]*n1.
+  std::vector<int64_t> pre_asc[3];
+  bool have_pre = false;
+  int32_t us_presort = 0;
+  if (argsort && thr_to_int(thr[0]) >= 2 && thr_to_int(thr[1]) >= 2 && n_cand[0] + n_cand[1] > 0) {
+    const clk::time_point t0 = clk::now();
+    std::vector<uint8_t> keys[2];
+    for (int m = 0; m < 2; ++m) {
+      keys[m].resize(n_cand[m]);
+      if (n_cand[m])
+        SRB_CUDA_OK(cudaMemcpyAsync(keys[m].data(), g->cand_score[m].p, n_cand[m], cudaMemcpyDeviceToHost, st));
+    }
+    SRB_CUDA_OK(cudaStreamSynchronize(st));
+    const int n3p = n_cand[0] + n_cand[1];
+    std::vector<double> pri(n3p);
+    for (int i = 0; i < n3p; ++i) pri[i] = i < n_cand[0] ? 1.0 : 0.0;
+    for (int m = 0; m < 2; ++m) pre_asc[m].resize(n_cand[m]);
+    pre_asc[2].resize(n3p);
+    int rcs[3] = {0, 0, 0};
+    std::thread th[3];
+    const void* kptr[3] = {keys[0].data(), keys[1].data(), pri.data()};
+    const int kdt[3] = {SAMROAD_U8, SAMROAD_U8, SAMROAD_F64};
+    const int64_t kn[3] = {n_cand[0], n_cand[1], n3p};
+    for (int i = 0; i < 3; ++i)
+      th[i] = std::thread([&, i] { rcs[i] = kn[i] ? argsort(kptr[i], kdt[i], kn[i], pre_asc[i].data(), user) : 0; });
+    for (int i = 0; i < 3; ++i) th[i].join();
+    SRB_REQUIRE(rcs[0] == 0 && rcs[1] == 0 && rcs[2] == 0, "argsort callback failed (%d %d %d)", rcs[0], rcs[1], rcs[2]);
+    have_pre = true;
+    us_presort = us_since(t0);
+  }
+
   // passes 1 and 2: per-mask NMS (graph_extraction.py:131-134)
   for (int m = 0; m < 2; ++m) {
     const int n = n_cand[m];
@@ -685,8 +723,8 @@ extern "C" int samroad_extract_graph_points(samroad_graph_t g, const uint8_t* ke
     if (int rc = g->sorted_pix.ensure(sizeof(int32_t) * static_cast<size_t>(n))) return rc;
     if (int rc = g->immune.ensure(static_cast<size_t>(n))) return rc;
     clk::time_point t0 = clk::now();
-    if (int rc = make_order_u8(g, g->cand_score[m].as<uint8_t>(), n, argsort, user, g->order.as<int32_t>(),
-                               tot + 4, st))
+    if (int rc = make_order_u8(g, g->cand_score[m].as<uint8_t>(), n, argsort, user,
+                               have_pre ? &pre_asc[m] : nullptr, g->order.as<int32_t>(), tot + 4, st))
       return rc;
     SRB_CUDA_OK(cudaMemsetAsync(tot + 5, 0, sizeof(int), st));
     gather_sorted_kernel<<<blocks_for(n), 256, 0, st>>>(g->cand_pix[m].as<int32_t>(), g->cand_score[m].as<uint8_t>(),
@@ -717,11 +755,16 @@ extern "C" int samroad_extract_graph_points(samroad_graph_t g, const uint8_t* ke
                                                   g->cand3.as<int32_t>());
     note_launch();
     if (argsort) {
-      std::vector<double> keys(n3);
-      for (int i = 0; i < n3; ++i) keys[i] = i < m0 ? 1.0 : 0.0;
-      std::vector<int64_t> asc(n3);
-      SRB_REQUIRE(argsort(keys.data(), SAMROAD_F64, n3, asc.data(), user) == 0,
-                  "argsort callback failed (float64 priorities)");
+      std::vector<int64_t> own3;
+      const bool pre3 = have_pre && m0 == n_cand[0] && m1 == n_cand[1];
+      if (!pre3) {
+        std::vector<double> keys(n3);
+        for (int i = 0; i < n3; ++i) keys[i] = i < m0 ? 1.0 : 0.0;
+        own3.resize(n3);
+        SRB_REQUIRE(argsort(keys.data(), SAMROAD_F64, n3, own3.data(), user) == 0,
+                    "argsort callback failed (float64 priorities)");
+      }
+      const std::vector<int64_t>& asc = pre3 ? pre_asc[2] : own3;
       if (int rc = g->ghist.ensure(sizeof(int64_t) * static_cast<size_t>(n3))) return rc;
       SRB_CUDA_OK(cudaMemcpyAsync(g->ghist.p, asc.data(), sizeof(int64_t) * n3, cudaMemcpyHostToDevice, st));
       order_from_host_kernel<<<blocks_for(n3), 256, 0, st>>>(g->ghist.as<int64_t>(), n3, g->order.as<int32_t>(),
@@ -757,7 +800,7 @@ extern "C" int samroad_extract_graph_points(samroad_graph_t g, const uint8_t* ke
     stats[0] = n_cand[0]; stats[1] = n_cand[1]; stats[2] = m0; stats[3] = m1;
     stats[4] = rounds[0]; stats[5] = rounds[1]; stats[6] = rounds[2]; stats[7] = n_out;
     // host wall-clock split in microseconds (each stage ends on a stream synchronisation)
-    stats[8] = us_cand; stats[9] = us_order[0]; stats[10] = us_order[1]; stats[11] = us_order[2];
+    stats[8] = us_cand; stats[9] = us_order[0] + us_presort; stats[10] = us_order[1]; stats[11] = us_order[2];
     stats[12] = us_nms[0]; stats[13] = us_nms[1]; stats[14] = us_nms[2]; stats[15] = us_since(t_begin);
   }
   return 0;
@@ -981,7 +1024,8 @@ namespace {
 // number of points within the neighbour radius of each point = upper bound of its distinct targets
 __global__ void __launch_bounds__(128)
 adj_kernel(const int32_t* __restrict__ pts, int N, int d2lt, const int* __restrict__ adj_off,
-           int* __restrict__ deg, int32_t* __restrict__ adj_src, int32_t* __restrict__ adj_tgt) {
+           int* __restrict__ deg, int32_t* __restrict__ adj_src, int32_t* __restrict__ adj_tgt,
+           int* __restrict__ max_deg) {
   __shared__ int sx[128], sy[128];
   const int i = blockIdx.x * 128 + threadIdx.x;
   int px = 0, py = 0;
@@ -1004,7 +1048,10 @@ adj_kernel(const int32_t* __restrict__ pts, int N, int d2lt, const int* __restri
     }
     __syncthreads();
   }
-  if (!adj_off && i < N) deg[i] = c;
+  if (!adj_off && i < N) {
+    deg[i] = c;
+    if (max_deg) atomicMax(max_deg, c);
+  }
 }
 
 __device__ __forceinline__ int lower_bound_i32(const int32_t* a, int n, int v) {
@@ -1016,9 +1063,74 @@ __device__ __forceinline__ int lower_bound_i32(const int32_t* a, int n, int v) {
   return lo;
 }
 
-// One thread per source point walks its tiles in tile-list order and its pair slots in order: for a
-// fixed (src, tgt) that is exactly the order in which the reference's triple loop adds the scores,
-// so the float32 sum is bit-identical.  first[] records the key's first occurrence in the loop.
+// One WARP per source point walks its tiles in tile-list order and its pair slots in order: for a fixed
+// (src, tgt) that is exactly the order in which the reference's triple loop adds the scores, so the
+// float32 sum is bit-identical.  The lanes own the source's adjacency slots (slot = lane + 32 d) and keep
+// sum / count / first occurrence in registers; a tile's K (target, score) pairs are loaded by K lanes at
+// once and broadcast one by one.  first[] records the key's first occurrence in the loop (dict order).
+template <int DPL>
+__global__ void __launch_bounds__(256)
+aggregate_warp_kernel(const int32_t* __restrict__ pts, int N, const int32_t* __restrict__ txy, int n_tiles, int P,
+                      const int* __restrict__ cnt, const int* __restrict__ off, const int32_t* __restrict__ members,
+                      const int32_t* __restrict__ nbr, const float* __restrict__ scores,
+                      const int64_t* __restrict__ tile_soff, int K, const int* __restrict__ adj_off,
+                      const int32_t* __restrict__ adj_tgt, float* __restrict__ sum, float* __restrict__ num,
+                      int32_t* __restrict__ first, int* __restrict__ bad) {
+  const int S = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (S >= N) return;
+  const int px = pts[2 * S], py = pts[2 * S + 1];
+  const int a0 = adj_off[S], deg = adj_off[S + 1] - a0;
+  int tg[DPL], fi[DPL];
+  float sm[DPL], nm[DPL];
+#pragma unroll
+  for (int d = 0; d < DPL; ++d) {
+    const int sl = lane + 32 * d;
+    tg[d] = sl < deg ? adj_tgt[a0 + sl] : -2;
+    fi[d] = -1; sm[d] = 0.f; nm[d] = 0.f;
+  }
+  bool badv = false;
+  for (int t = 0; t < n_tiles; ++t) {
+    if (!in_tile(px, py, txy[2 * t], txy[2 * t + 1], P)) continue;
+    const int64_t so = tile_soff[t];
+    if (so < 0) continue;                                   // batch skipped: no points (inferencer.py:188-189)
+    const int base = off[t];
+    const int j = lower_bound_i32(members + base, cnt[t], S);
+    int Tk = -1;
+    float vk = 0.f;
+    if (lane < K) {
+      const int nb = nbr[(static_cast<size_t>(base) + j) * 16 + lane];
+      if (nb >= 0) {
+        Tk = members[base + nb];
+        vk = scores[so + static_cast<int64_t>(j) * K + lane];
+      }
+    }
+    for (int k = 0; k < K; ++k) {
+      const int T = __shfl_sync(0xffffffffu, Tk, k);
+      if (T < 0) break;                                      // prefix-valid
+      float v = __shfl_sync(0xffffffffu, vk, k);
+      if (v != v) v = -100.0f;                               // inferencer.py:206
+      if (!(v >= 0.0f && v <= 1.0f)) badv = true;            // the reference asserts (inferencer.py:219)
+#pragma unroll
+      for (int d = 0; d < DPL; ++d) {
+        if (tg[d] == T) {
+          sm[d] = __fadd_rn(sm[d], v);
+          nm[d] = __fadd_rn(nm[d], 1.0f);
+          if (fi[d] < 0) fi[d] = (base + j) * K + k;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < DPL; ++d) {
+    const int sl = lane + 32 * d;
+    if (sl < deg) { sum[a0 + sl] = sm[d]; num[a0 + sl] = nm[d]; first[a0 + sl] = fi[d]; }
+  }
+  if (badv && lane == 0) atomicOr(bad, 1);
+}
+
+// Fallback for sources with more than 128 points within the neighbour radius (tiny NMS radii): one thread per
+// source, slots in global memory.  Same order of additions.
 __global__ void __launch_bounds__(128)
 aggregate_kernel(const int32_t* __restrict__ pts, int N, const int32_t* __restrict__ txy, int n_tiles, int P,
                  const int* __restrict__ cnt, const int* __restrict__ off, const int32_t* __restrict__ members,
@@ -1080,11 +1192,15 @@ extern "C" int samroad_aggregate_edges(samroad_graph_t g, const float* topo_scor
   if (int rc = g->tile_soff.ensure(sizeof(int64_t) * g->n_tiles)) return rc;
   SRB_CUDA_OK(cudaMemcpyAsync(g->tile_soff.p, tile_score_offset_host, sizeof(int64_t) * g->n_tiles,
                               cudaMemcpyHostToDevice, st));
-  adj_kernel<<<blocks_for(N, 128), 128, 0, st>>>(pts, N, g->d2lt, nullptr, g->adj_deg.as<int>(), nullptr, nullptr);
-  scan_single_block_kernel<<<1, 1024, 0, st>>>(g->adj_deg.as<int>(), N, g->adj_off.as<int>(), g->adj_off.as<int>() + N);
+  int* tot = g->totals.as<int>();
+  SRB_CUDA_OK(cudaMemsetAsync(tot + 8, 0, 4 * sizeof(int), st));
+  adj_kernel<<<blocks_for(N, 128), 128, 0, st>>>(pts, N, g->d2lt, nullptr, g->adj_deg.as<int>(), nullptr, nullptr, tot + 10);
+  scan_single_block_kernel<<<1, 1024, 0, st>>>(g->adj_deg.as<int>(), N, g->adj_off.as<int>(), tot + 11);
   note_launch(2);
-  int nnz = 0;
-  if (int rc = read_ints(g, g->adj_off.as<int>() + N, 1, &nnz, st)) return rc;
+  int degs[2];
+  if (int rc = read_ints(g, tot + 10, 2, degs, st)) return rc;
+  const int max_deg = degs[0], nnz = degs[1];
+  SRB_CUDA_OK(cudaMemcpyAsync(g->adj_off.as<int>() + N, tot + 11, sizeof(int), cudaMemcpyDeviceToDevice, st));
   if (nnz == 0) return 0;
   const size_t nz = static_cast<size_t>(nnz);
   if (int rc = g->adj_src.ensure(4 * nz)) return rc;
@@ -1094,19 +1210,26 @@ extern "C" int samroad_aggregate_edges(samroad_graph_t g, const float* topo_scor
   if (int rc = g->adj_first.ensure(4 * nz)) return rc;
   const long n_entries = g->total * K;
   if (int rc = g->eflags.ensure(4 * static_cast<size_t>(n_entries))) return rc;
-  int* tot = g->totals.as<int>();
   SRB_CUDA_OK(cudaMemsetAsync(g->adj_sum.p, 0, 4 * nz, st));
   SRB_CUDA_OK(cudaMemsetAsync(g->adj_cnt.p, 0, 4 * nz, st));
   SRB_CUDA_OK(cudaMemsetAsync(g->adj_first.p, 0xFF, 4 * nz, st));
   SRB_CUDA_OK(cudaMemsetAsync(g->eflags.p, 0xFF, 4 * static_cast<size_t>(n_entries), st));
-  SRB_CUDA_OK(cudaMemsetAsync(tot + 8, 0, 2 * sizeof(int), st));
   adj_kernel<<<blocks_for(N, 128), 128, 0, st>>>(pts, N, g->d2lt, g->adj_off.as<int>(), nullptr,
-                                                 g->adj_src.as<int32_t>(), g->adj_tgt.as<int32_t>());
-  aggregate_kernel<<<blocks_for(N, 128), 128, 0, st>>>(
-      pts, N, g->tile_xy.as<int32_t>(), g->n_tiles, g->P, g->t_cnt.as<int>(), g->t_off.as<int>(),
-      g->members.as<int32_t>(), g->nbr.as<int32_t>(), topo_scores, g->tile_soff.as<int64_t>(), K,
-      g->adj_off.as<int>(), g->adj_tgt.as<int32_t>(), g->adj_sum.as<float>(), g->adj_cnt.as<float>(),
-      g->adj_first.as<int32_t>(), tot + 8);
+                                                 g->adj_src.as<int32_t>(), g->adj_tgt.as<int32_t>(), nullptr);
+#define SRB_AGG_ARGS                                                                                         \
+  pts, N, g->tile_xy.as<int32_t>(), g->n_tiles, g->P, g->t_cnt.as<int>(), g->t_off.as<int>(),               \
+      g->members.as<int32_t>(), g->nbr.as<int32_t>(), topo_scores, g->tile_soff.as<int64_t>(), K,           \
+      g->adj_off.as<int>(), g->adj_tgt.as<int32_t>(), g->adj_sum.as<float>(), g->adj_cnt.as<float>(),       \
+      g->adj_first.as<int32_t>(), tot + 8
+  if (max_deg <= 32)
+    aggregate_warp_kernel<1><<<blocks_for(32L * N, 256), 256, 0, st>>>(SRB_AGG_ARGS);
+  else if (max_deg <= 64)
+    aggregate_warp_kernel<2><<<blocks_for(32L * N, 256), 256, 0, st>>>(SRB_AGG_ARGS);
+  else if (max_deg <= 128)
+    aggregate_warp_kernel<4><<<blocks_for(32L * N, 256), 256, 0, st>>>(SRB_AGG_ARGS);
+  else
+    aggregate_kernel<<<blocks_for(N, 128), 128, 0, st>>>(SRB_AGG_ARGS);
+#undef SRB_AGG_ARGS
   edge_select_kernel<<<blocks_for(nnz), 256, 0, st>>>(g->adj_sum.as<float>(), g->adj_cnt.as<float>(),
                                                       g->adj_first.as<int32_t>(), nnz, threshold,
                                                       g->eflags.as<int32_t>());

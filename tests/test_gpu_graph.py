@@ -176,16 +176,18 @@ def _reference_edge_loop(ref, batches, scores_by_tile, K):
     return es, ec
 
 
-@pytest.mark.parametrize("grid,world", [((400, 0, 256, 4), 1), ((400, 0, 256, 16), 2), ((2048, 64, 512, 16), 1),
-                                        ((2048, 64, 512, 8), 4)])
-def test_edge_aggregation_bit_exact(gx, grid, world):
+@pytest.mark.parametrize("grid,world,min_dist", [((400, 0, 256, 4), 1, 10), ((400, 0, 256, 16), 2, 10),
+                                                 ((2048, 64, 512, 16), 1, 17), ((2048, 64, 512, 8), 4, 17),
+                                                 ((400, 0, 256, 4), 1, 6),      # 64 < neighbours in range <= 128
+                                                 ((400, 0, 256, 4), 2, 3)])     # > 128: one-thread-per-source fallback
+def test_edge_aggregation_bit_exact(gx, grid, world, min_dist):
     """Random float32 scores through the device aggregation vs the reference triple loop: identical
     edges in identical (dict insertion) order for several thresholds; the score-buffer layout is the
     one infer_one_img uses (per batch [n, nmax_of_batch, K], batch plan of `world` ranks)."""
     size, margin, P, per_edge = grid
     rng = np.random.RandomState(3 * size + per_edge)
     tiles = get_patch_info_one_img(0, size, margin, P, per_edge)
-    pts = _nms_like_points(rng, size, 700 if size == 400 else 4000, 10 if size == 400 else 17)
+    pts = _nms_like_points(rng, size, (700 if min_dist >= 10 else 6000) if size == 400 else 4000, min_dist)
     pts = pts[~((pts[:, 0] > size * 0.7) & (pts[:, 1] > size * 0.6))]       # an empty corner: empty tiles
     K, R, bs = 16, 64.0, 64 if size > 400 else 6
     txy = np.array([t[1] for t in tiles], dtype=np.int32)
