@@ -626,6 +626,12 @@ extern "C" int samroad_finalize_weights(samroad_handle_t h) {
     if (const HostTensor* wt = P.get(md + "output_upscaling.3.weight", {64, 32, 2, 2}))
       S.up2_w = P.upload(pack_convT(*wt, 64, 32));
     if (const HostTensor* bt = P.get(md + "output_upscaling.3.bias", {32})) S.up2_b = P.upload(tile4(bt->data));
+    if (P.ok) {   // constant part of the decoder: layer-0 queries
+      float* q0 = P.upload(std::vector<float>(4 * 256, 0.f));
+      if (q0 && (sam_decoder_prepare(S, q0, nullptr) != 0 || cudaStreamSynchronize(nullptr) != cudaSuccess))
+        P.fail("sam_decoder_prepare failed: %s", get_last_error());
+      S.q0 = q0;
+    }
   }
 
   // ---- TopoNet (model.py:61-86) ----

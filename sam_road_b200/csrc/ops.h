@@ -110,6 +110,7 @@ int topo_transformer_fused(const TopoPairInputs& in, const __half* w_chunks, con
 struct SamAttnW { const float *qw, *qb, *kw, *kb, *vw, *vb, *ow, *ob; };
 struct SamDecoderWeights {
   const float* tokens;        // [4][256] = [iou_token ; mask_tokens]
+  const float* q0;            // [4][256] = norm1(self_attn(tokens)) of layer 0 (sam_decoder_prepare)
   const float* no_mask_embed; // [256]
   const float* dense_pe;      // [T][256]
   SamAttnW self_attn[2], t2i[2], i2t[2], final_attn;
@@ -124,6 +125,7 @@ struct SamDecoderWeights {
   const float *up1_b, *up1_g, *up1_beta, *up2_b;
 };
 size_t sam_decoder_ws_bytes(int B, int T);
+int sam_decoder_prepare(const SamDecoderWeights& w, float* q0_out, cudaStream_t st);
 int sam_decoder_forward(const SamDecoderWeights& w, const float* emb_nchw, int B, int s, int P, void* ws,
                         float* mask_scores, float* mask_logits, cudaStream_t st);
 
