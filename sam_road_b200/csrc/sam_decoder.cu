@@ -110,65 +110,6 @@ struct SamLayerW {
   const float *l1w, *l1b, *l2w, *l2b;
 };
 
-// token -> image attention for one image: q4 [4][128] (already projected), K/V [T][128] fp32 of this
-// image, 8 heads x 16; 256 threads = 32 (token, head) pairs x 8 key partitions, online softmax, then
-// a cross-partition merge in shared memory.  out [4][128].
-__device__ void block_t2i_attention(const float* q4, const float* __restrict__ K,
-                                    const float* __restrict__ V, int T, float* out, float* red) {
-  const int pair = threadIdx.x >> 3, part = threadIdx.x & 7;
-  const int i = pair >> 3, h = pair & 7;
-  float q[16];
-#pragma unroll
-  for (int d = 0; d < 16; ++d) q[d] = q4[i * 128 + h * 16 + d] * 0.25f;   // / sqrt(16)
-  float m = -INFINITY, l = 0.f, o[16];
-#pragma unroll
-  for (int d = 0; d < 16; ++d) o[d] = 0.f;
-  for (int t = part; t < T; t += 8) {
-    const float4* kp = reinterpret_cast<const float4*>(K + static_cast<size_t>(t) * 128 + h * 16);
-    float s = 0.f;
-#pragma unroll
-    for (int d4 = 0; d4 < 4; ++d4) {
-      const float4 kv = __ldg(kp + d4);
-      s = fmaf(q[4 * d4], kv.x, s); s = fmaf(q[4 * d4 + 1], kv.y, s);
-      s = fmaf(q[4 * d4 + 2], kv.z, s); s = fmaf(q[4 * d4 + 3], kv.w, s);
-    }
-    const float mn = fmaxf(m, s);
-    const float a = expf(m - mn), p = expf(s - mn);
-    l = l * a + p;
-    const float4* vp = reinterpret_cast<const float4*>(V + static_cast<size_t>(t) * 128 + h * 16);
-#pragma unroll
-    for (int d4 = 0; d4 < 4; ++d4) {
-      const float4 vv = __ldg(vp + d4);
-      o[4 * d4] = fmaf(p, vv.x, o[4 * d4] * a); o[4 * d4 + 1] = fmaf(p, vv.y, o[4 * d4 + 1] * a);
-      o[4 * d4 + 2] = fmaf(p, vv.z, o[4 * d4 + 2] * a); o[4 * d4 + 3] = fmaf(p, vv.w, o[4 * d4 + 3] * a);
-    }
-    m = mn;
-  }
-  // merge the 8 partitions of each pair: red[pair][part][18] = {m, l, o[16]}
-  float* r = red + (pair * 8 + part) * 18;
-  r[0] = m; r[1] = l;
-#pragma unroll
-  for (int d = 0; d < 16; ++d) r[2 + d] = o[d];
-  __syncthreads();
-  if (part == 0) {
-    float M = -INFINITY;
-    for (int pp = 0; pp < 8; ++pp) M = fmaxf(M, red[(pair * 8 + pp) * 18]);
-    float L = 0.f, O[16];
-#pragma unroll
-    for (int d = 0; d < 16; ++d) O[d] = 0.f;
-    for (int pp = 0; pp < 8; ++pp) {
-      const float* rr = red + (pair * 8 + pp) * 18;
-      const float a = rr[0] == -INFINITY ? 0.f : expf(rr[0] - M);
-      L = fmaf(rr[1], a, L);
-#pragma unroll
-      for (int d = 0; d < 16; ++d) O[d] = fmaf(rr[2 + d], a, O[d]);
-    }
-#pragma unroll
-    for (int d = 0; d < 16; ++d) out[i * 128 + h * 16 + d] = O[d] / L;
-  }
-  __syncthreads();
-}
-
 // ------------------------------------------------------------------------------------------------
 // layer-0 self-attention on the (batch independent) output tokens: queries0 = norm1(self_attn(tok))
 // ------------------------------------------------------------------------------------------------
@@ -197,54 +138,71 @@ struct SamFinalW {
 // ------------------------------------------------------------------------------------------------
 // batched token side: every kernel below works on the [Bt = 4B, C] fp32 token matrix of all images
 // ------------------------------------------------------------------------------------------------
-// out[m][n] = act(sum_k (A[m][k] + pe[m % 4][k]) * W[n][k] + b[n]); fp32 SIMT, 64x64 output tile per CTA,
-// 16-deep k slabs in shared memory, 4x4 outputs per thread.  pe may be null; M, N, K arbitrary.
+// out[m][n] = act(sum_k (A[m][k] + pe[m % 4][k]) * W[n][k] + b[n]); fp32 SIMT.  A CTA owns a 32 x 64 output
+// tile (2 x 4 outputs per thread); the k dimension is walked in slabs of 16 through shared memory, each
+// thread fetching one float4 of W (and half the threads one of A) for the NEXT slab before it computes the
+// current one, so the global-load latency hides under the FMAs.  K % 4 == 0; pe may be null.
 __global__ void __launch_bounds__(256)
 tok_gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ pe, int ldpe,
                 const float* __restrict__ W, const float* __restrict__ bias, int M, int N, int K, int relu,
                 float* __restrict__ out, int ldo) {
-  __shared__ float As[16][64 + 1], Ws[16][64 + 1];
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // 16 x 16 threads, 4 x 4 outputs each
-  float acc[4][4];
+  __shared__ float As[2][16][32 + 1], Ws[2][16][64 + 1];
+  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // 16 x 16 threads: rows ty*2.., cols tx*4..
+  const int lr = threadIdx.x >> 2, lk = (threadIdx.x & 3) * 4;  // loader: row lr (0..63), k offset lk
+  float acc[2][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
-      const int r = i >> 4, kk = i & 15;
-      const int m = m0 + r, n = n0 + r, k = k0 + kk;
-      float a = 0.f, w = 0.f;
-      if (k < K) {
-        if (m < M) a = A[static_cast<size_t>(m) * lda + k] + (pe ? __ldg(pe + (m & 3) * ldpe + k) : 0.f);
-        if (n < N) w = __ldg(W + static_cast<size_t>(n) * K + k);
+  auto fetch = [&](int k0, float4& a, float4& w) {
+    a = make_float4(0.f, 0.f, 0.f, 0.f);
+    w = a;
+    const int k = k0 + lk;
+    if (k < K) {
+      if (lr < 32 && m0 + lr < M) {
+        a = *reinterpret_cast<const float4*>(A + static_cast<size_t>(m0 + lr) * lda + k);
+        if (pe) {
+          const float4 p4 = __ldg(reinterpret_cast<const float4*>(pe + ((m0 + lr) & 3) * ldpe + k));
+          a.x += p4.x; a.y += p4.y; a.z += p4.z; a.w += p4.w;
+        }
       }
-      As[kk][r] = a;
-      Ws[kk][r] = w;
+      if (n0 + lr < N) w = __ldg(reinterpret_cast<const float4*>(W + static_cast<size_t>(n0 + lr) * K + k));
     }
-    __syncthreads();
+  };
+  auto stash = [&](int buf, const float4& a, const float4& w) {
+    if (lr < 32) { As[buf][lk][lr] = a.x; As[buf][lk + 1][lr] = a.y; As[buf][lk + 2][lr] = a.z; As[buf][lk + 3][lr] = a.w; }
+    Ws[buf][lk][lr] = w.x; Ws[buf][lk + 1][lr] = w.y; Ws[buf][lk + 2][lr] = w.z; Ws[buf][lk + 3][lr] = w.w;
+  };
+  float4 a4, w4;
+  fetch(0, a4, w4);
+  stash(0, a4, w4);
+  __syncthreads();
+  const int nslab = (K + 15) / 16;
+  for (int sI = 0; sI < nslab; ++sI) {
+    const int buf = sI & 1;
+    if (sI + 1 < nslab) fetch((sI + 1) * 16, a4, w4);          // in flight while this slab is multiplied
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
-      float a[4], w[4];
+      const float a0 = As[buf][kk][ty * 2], a1 = As[buf][kk][ty * 2 + 1];
+      float w[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; w[i] = Ws[kk][tx * 4 + i]; }
+      for (int j = 0; j < 4; ++j) w[j] = Ws[buf][kk][tx * 4 + j];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+      for (int j = 0; j < 4; ++j) { acc[0][j] = fmaf(a0, w[j], acc[0][j]); acc[1][j] = fmaf(a1, w[j], acc[1][j]); }
     }
+    if (sI + 1 < nslab) stash(buf ^ 1, a4, w4);
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+  for (int i = 0; i < 2; ++i) {
+    const int m = m0 + ty * 2 + i;
     if (m >= M) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
       if (n >= N) continue;
-      float v = acc[i][j] + (bias ? __ldg(bias + n) : 0.f);
+      const float v = acc[i][j] + (bias ? __ldg(bias + n) : 0.f);
       out[static_cast<size_t>(m) * ldo + n] = relu ? fmaxf(v, 0.f) : v;
     }
   }
@@ -253,7 +211,9 @@ tok_gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ 
 int tok_gemm(const float* A, int lda, const float* pe, const float* W, const float* bias, int M, int N, int K,
              bool relu, float* out, int ldo, cudaStream_t st) {
   if (M <= 0) return 0;
-  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  SRB_REQUIRE(K % 4 == 0 && lda % 4 == 0 && (reinterpret_cast<uintptr_t>(A) & 15u) == 0,
+              "tok_gemm: K=%d lda=%d must be multiples of 4 and A 16-byte aligned", K, lda);
+  dim3 grid((N + 63) / 64, (M + 31) / 32);
   tok_gemm_kernel<<<grid, 256, 0, st>>>(A, lda, pe, kC, W, bias, M, N, K, relu ? 1 : 0, out, ldo);
   SRB_CUDA_OK(cudaGetLastError());
   note_launch();
@@ -320,16 +280,60 @@ tok_self_attention_kernel(const float* __restrict__ q, const float* __restrict__
   out[idx] = o / l;
 }
 
-// token -> image attention, one CTA per image (block_t2i_attention on global operands)
+// token -> image attention, one CTA per (image, head): 4 tokens x 64 key partitions = 256 threads, online
+// softmax per partition, then a shared-memory merge of the 64 partitions of each token.  q [Bt][128]
+// (projected queries), K32 / V32 [B*T][128] fp32, 8 heads x 16; out [Bt][128].
 __global__ void __launch_bounds__(kThreads)
-tok_t2i_attention_kernel(const float* __restrict__ q /* [Bt][128] */, const float* __restrict__ K32,
-                         const float* __restrict__ V32, int T, float* __restrict__ out /* [Bt][128] */) {
-  __shared__ float q4[kTok * 128], o4[kTok * 128], red[32 * 8 * 18];
-  const int b = blockIdx.x;
-  for (int i = threadIdx.x; i < kTok * 128; i += blockDim.x) q4[i] = q[static_cast<size_t>(b) * kTok * 128 + i];
+tok_t2i_attention_kernel(const float* __restrict__ qg, const float* __restrict__ K32,
+                         const float* __restrict__ V32, int T, float* __restrict__ out) {
+  __shared__ float red[kTok][64][18];
+  const int b = blockIdx.x, h = blockIdx.y;
+  const int i = threadIdx.x >> 6, part = threadIdx.x & 63;
+  const float* K = K32 + static_cast<size_t>(b) * T * 128 + h * 16;
+  const float* V = V32 + static_cast<size_t>(b) * T * 128 + h * 16;
+  float q[16];
+#pragma unroll
+  for (int d = 0; d < 16; ++d) q[d] = qg[(static_cast<size_t>(b) * kTok + i) * 128 + h * 16 + d] * 0.25f;   // / sqrt(16)
+  float m = -INFINITY, l = 0.f, o[16];
+#pragma unroll
+  for (int d = 0; d < 16; ++d) o[d] = 0.f;
+  for (int t = part; t < T; t += 64) {
+    const float4* kp = reinterpret_cast<const float4*>(K + static_cast<size_t>(t) * 128);
+    float sc = 0.f;
+#pragma unroll
+    for (int d4 = 0; d4 < 4; ++d4) {
+      const float4 kv = __ldg(kp + d4);
+      sc = fmaf(q[4 * d4], kv.x, sc); sc = fmaf(q[4 * d4 + 1], kv.y, sc);
+      sc = fmaf(q[4 * d4 + 2], kv.z, sc); sc = fmaf(q[4 * d4 + 3], kv.w, sc);
+    }
+    const float mn = fmaxf(m, sc);
+    const float a = expf(m - mn), p = expf(sc - mn);
+    l = l * a + p;
+    const float4* vp = reinterpret_cast<const float4*>(V + static_cast<size_t>(t) * 128);
+#pragma unroll
+    for (int d4 = 0; d4 < 4; ++d4) {
+      const float4 vv = __ldg(vp + d4);
+      o[4 * d4] = fmaf(p, vv.x, o[4 * d4] * a); o[4 * d4 + 1] = fmaf(p, vv.y, o[4 * d4 + 1] * a);
+      o[4 * d4 + 2] = fmaf(p, vv.z, o[4 * d4 + 2] * a); o[4 * d4 + 3] = fmaf(p, vv.w, o[4 * d4 + 3] * a);
+    }
+    m = mn;
+  }
+  float* r = red[i][part];
+  r[0] = m; r[1] = l;
+#pragma unroll
+  for (int d = 0; d < 16; ++d) r[2 + d] = o[d];
   __syncthreads();
-  block_t2i_attention(q4, K32 + static_cast<size_t>(b) * T * 128, V32 + static_cast<size_t>(b) * T * 128, T, o4, red);
-  for (int i = threadIdx.x; i < kTok * 128; i += blockDim.x) out[static_cast<size_t>(b) * kTok * 128 + i] = o4[i];
+  if (part < 16) {          // thread (token i, channel part) merges the 64 partitions for its channel
+    float Mx = -INFINITY;
+    for (int pp = 0; pp < 64; ++pp) Mx = fmaxf(Mx, red[i][pp][0]);
+    float L = 0.f, O = 0.f;
+    for (int pp = 0; pp < 64; ++pp) {
+      const float a = red[i][pp][0] == -INFINITY ? 0.f : expf(red[i][pp][0] - Mx);
+      L = fmaf(red[i][pp][1], a, L);
+      O = fmaf(red[i][pp][2 + part], a, O);
+    }
+    out[(static_cast<size_t>(b) * kTok + i) * 128 + h * 16 + part] = O / L;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -535,7 +539,7 @@ int sam_decoder_forward(const SamDecoderWeights& W, const float* emb_nchw, int B
   auto t2i = [&](const AttnW& a, const float* g, const float* bb) -> int {
     // queries = norm(queries + out_proj(softmax(q_proj(queries + pe) K^T / 4) V))   (transformer.py:168-172,99-104)
     if (int rc = tok_gemm(b.X, kC, pe, a.qw, a.qb, Bt, 128, kC, false, b.Qc, 128, st)) return rc;
-    tok_t2i_attention_kernel<<<B, kThreads, 0, st>>>(b.Qc, b.K32, b.V32, T, b.A2);
+    tok_t2i_attention_kernel<<<dim3(B, 8), kThreads, 0, st>>>(b.Qc, b.K32, b.V32, T, b.A2);
     note_launch();
     if (int rc = tok_gemm(b.A2, 128, nullptr, a.ow, a.ob, Bt, kC, 128, false, b.T1, kC, st)) return rc;
     LN(b.X, b.T1, g, bb);
