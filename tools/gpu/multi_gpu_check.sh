@@ -12,3 +12,12 @@ for tag, s in (d.get('e2e_scene') or {}).items():
     for tie in ('numpy', 'stable'):
         print(tag, tie, round(s[tie]['value'], 1), 'tiles/s', round(s[tie]['ms_per_scene'], 2), 'ms', s[tie]['stages_ms'])
 PY
+# A/B: the same step without the exchange (what the slowest GPU alone costs)
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --steps 20 --warmup 3 --no-exchange --no-scene --no-cpu-baseline > gpurun_out/bench_n${N}_noex.json 2> gpurun_out/bench_n${N}_noex.err
+python - <<PY
+import json
+d = json.loads(open('gpurun_out/bench_n${N}_noex.json').readline())
+print('NO-EXCHANGE N', d['n_gpus'], 'value', round(d['value'], 1), 'per gpu', round(d['value'] / d['n_gpus'], 1), 'ms/step', round(d['ms_per_step'], 3), 'by rank', d['ms_per_step_by_rank'])
+d = json.loads(open('gpurun_out/bench_n$N.json').readline())
+print('WITH EXCHANGE by rank', d['ms_per_step_by_rank'], d['config']['exchange'])
+PY
