@@ -124,9 +124,12 @@ struct samroad_ctx {
   __half* tp_chunks = nullptr;   // fused-kernel weight chunks [18*128, 128]
   float* tp_out_w = nullptr; float* tp_out_b = nullptr;
 
-  // activation workspace (grown on demand)
+  // activation workspace (grown on demand); TopoNet has its own so that the encoder of the next scene
+  // (another stream) can run while the TopoNet pass of the previous one is still in flight
   void* ws = nullptr;
   size_t ws_bytes = 0;
+  void* topo_ws = nullptr;
+  size_t topo_ws_bytes = 0;
   // staging for the host-buffer entry points: two slots so that step i's downloads overlap step
   // i+1's upload and compute (samroad_infer_batch_host_async / _wait)
   struct HostSlot {
@@ -399,6 +402,7 @@ extern "C" int samroad_destroy(samroad_handle_t h) {
   cudaDeviceSynchronize();
   for (void* p : h->weight_allocs) cudaFree(p);
   if (h->ws) cudaFree(h->ws);
+  if (h->topo_ws) cudaFree(h->topo_ws);
   if (h->sam_ws) cudaFree(h->sam_ws);
   if (h->s_compute) { cudaStreamDestroy(h->s_h2d); cudaStreamDestroy(h->s_compute); cudaStreamDestroy(h->s_copy); }
   for (auto& sl : h->slots) {
@@ -866,9 +870,8 @@ extern "C" int samroad_toponet(samroad_handle_t h, const float* image_embeddings
   SRB_REQUIRE(tokl < 2147483647L / 4, "samroad_toponet: %ld pair tokens is too many for one call",
               tokl);
   const int tok = static_cast<int>(tokl), pts = B * N, rows = B * Ns;
-  // TopoNet shares the activation workspace with the encoder (calls are stream-ordered)
-  SRB_TRY(ensure_bytes(&h->ws, &h->ws_bytes, layout_topo(B, N, Ns, Np, nullptr).total));
-  TopoWs w = layout_topo(B, N, Ns, Np, h->ws);
+  SRB_TRY(ensure_bytes(&h->topo_ws, &h->topo_ws_bytes, layout_topo(B, N, Ns, Np, nullptr).total));
+  TopoWs w = layout_topo(B, N, Ns, Np, h->topo_ws);
   const int zero_off = h->cfg.toponet_version == SAMROAD_TOPO_NO_OFFSET;
   const bool no_tf = h->cfg.toponet_version == SAMROAD_TOPO_NO_TRANSFORMER;
 
@@ -1016,7 +1019,7 @@ extern "C" int samroad_infer_batch_host_async(samroad_handle_t h, int slot, cons
   SRB_TRY(ensure_bytes(reinterpret_cast<void**>(&sl.emb), &sl.emb_bytes, em_bytes));
   // the activation workspace is shared by both slots: grow it before anything is in flight on it
   SRB_TRY(ensure_bytes(&h->ws, &h->ws_bytes, layout_enc(h, B, nullptr).total));
-  if (topo) SRB_TRY(ensure_bytes(&h->ws, &h->ws_bytes, layout_topo(B, N, Ns, Np, nullptr).total));
+  if (topo) SRB_TRY(ensure_bytes(&h->topo_ws, &h->topo_ws_bytes, layout_topo(B, N, Ns, Np, nullptr).total));
   char* base = static_cast<char*>(sl.in);
   cudaStream_t su = h->s_h2d, st = h->s_compute, sc = h->s_copy;
   // upload: the slot's input staging was last read by the slot's previous compute

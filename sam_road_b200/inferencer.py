@@ -90,16 +90,18 @@ def _exchange(rows_per_rank: int, P: int, device: torch.device, group, world: in
         _EXCHANGES.clear()
         _EXCHANGES[key] = TileExchange(rows_per_rank, (P, P, 2), torch.float32, device, group=group, slots=1)
     return _EXCHANGES[key]
-_PINNED: Dict[Tuple[int, int], Tuple[torch.Tensor, torch.Tensor]] = {}
+_PINNED: Dict[Tuple[int, int, int], Tuple[torch.Tensor, torch.Tensor]] = {}
 
 
-def _pinned_masks(H: int, W: int):
-    """Page-locked staging for the two uint8 masks (allocated once per scene size; the caller gets copies)."""
-    if (H, W) not in _PINNED:
-        _PINNED.clear()
-        _PINNED[(H, W)] = (torch.empty((H, W), dtype=torch.uint8).pin_memory(),
-                           torch.empty((H, W), dtype=torch.uint8).pin_memory())
-    return _PINNED[(H, W)]
+def _pinned_masks(H: int, W: int, slot: int = 0):
+    """Page-locked staging for the two uint8 masks (allocated once per scene size and pipeline slot; the
+    caller gets copies)."""
+    if (H, W, slot) not in _PINNED:
+        for k in [k for k in _PINNED if k[:2] != (H, W)]:
+            del _PINNED[k]
+        _PINNED[(H, W, slot)] = (torch.empty((H, W), dtype=torch.uint8).pin_memory(),
+                                 torch.empty((H, W), dtype=torch.uint8).pin_memory())
+    return _PINNED[(H, W, slot)]
 
 
 def _scene_graph(device: torch.device) -> SceneGraph:
@@ -109,37 +111,33 @@ def _scene_graph(device: torch.device) -> SceneGraph:
     return _GRAPHS[idx]
 
 
-def infer_one_img(net, img: np.ndarray, config, device: Optional[torch.device] = None,
-                  group=None, timings: Optional[dict] = None, shard: bool = True,
-                  nms_tie_order: Optional[str] = None):
-    """Whole-scene inference (inferencer.py:61-234).
+class _SceneJob:
+    """State of one scene between its two halves (pass 1 enqueued -> graph stage / pass 2)."""
+    pass
 
-    img: uint8 [H,W,3] RGB.  Returns (pred_nodes int64 [N,2] (r,c), pred_edges int64 [E,2],
-    fused_keypoint_mask uint8 [H,W], fused_road_mask uint8 [H,W]) -- identical on every rank when run
-    distributed.  `shard=False` makes a rank process the whole scene alone even if torch.distributed
-    is up.  `nms_tie_order`: "numpy" (default; this host's np.argsort decides ties like the reference)
-    or "stable" (device-only sort), see sam_road_b200.graph."""
+
+def _scene_start(net, img: np.ndarray, config, device: torch.device, group, shard: bool, slot: int = 0) -> _SceneJob:
+    """First half of infer_one_img (inferencer.py:61-110), enqueue only: scene upload, pass 1 over the
+    tiles this rank owns, the mask-score exchange, fusion and the start of the mask download -- all on the
+    current stream, no host synchronisation."""
     import torch.distributed as dist
+    j = _SceneJob()
     distributed = shard and dist.is_available() and dist.is_initialized()
-    rank = dist.get_rank(group) if distributed else 0
-    world = dist.get_world_size(group) if distributed else 1
-    if device is None:
-        device = next(net.parameters()).device
-    device = torch.device(device)
-    if device.type != "cuda":
-        raise RuntimeError(f"sam_road_b200.infer_one_img runs on CUDA only, got '{device}'")
-    t_start = time.perf_counter()
-
+    j.group = group
+    j.rank = rank = dist.get_rank(group) if distributed else 0
+    j.world = world = dist.get_world_size(group) if distributed else 1
+    j.device, j.net, j.config = device, net, config
+    j.t_start = time.perf_counter()
     H, W = int(img.shape[0]), int(img.shape[1])
-    P = int(_cfg_get(config, "PATCH_SIZE"))
+    j.P = P = int(_cfg_get(config, "PATCH_SIZE"))
     s = P // 16
-    bs = int(_cfg_get(config, "INFER_BATCH_SIZE"))
+    j.bs = bs = int(_cfg_get(config, "INFER_BATCH_SIZE"))
     tiles = get_patch_info_one_img(0, H, int(_cfg_get(config, "SAMPLE_MARGIN")), P,
                                    int(_cfg_get(config, "INFER_PATCHES_PER_EDGE")))
-    n_tiles = len(tiles)
-    tile_xy = np.array([t[1] for t in tiles], dtype=np.int32).reshape(-1, 2)
+    j.n_tiles = n_tiles = len(tiles)
+    j.tile_xy = tile_xy = np.array([t[1] for t in tiles], dtype=np.int32).reshape(-1, 2)
     lo, hi, per = _shard(n_tiles, rank, world)
-    n_mine = hi - lo
+    j.lo, n_mine = lo, hi - lo
 
     # ---- pass 1: masks + image features of the tiles this rank owns -------------------------------
     img_d = torch.as_tensor(np.ascontiguousarray(img)).to(device)               # one H2D of the scene
@@ -151,8 +149,8 @@ def infer_one_img(net, img: np.ndarray, config, device: Optional[torch.device] =
     else:
         scores_all = torch.empty((per, P, P, 2), dtype=torch.float32, device=device)
         my_scores = scores_all
-    feats = torch.empty((max(n_mine, 1), 256, s, s), dtype=torch.float32, device=device)
-    scene_call = getattr(net, "infer_masks_and_img_features_scene", None)
+    j.feats = feats = torch.empty((max(n_mine, 1), 256, s, s), dtype=torch.float32, device=device)
+    j.scene_call = scene_call = getattr(net, "infer_masks_and_img_features_scene", None)
     n_batches = (n_mine + bs - 1) // bs
     for bi, b0 in enumerate(range(0, n_mine, bs)):
         nb = min(bs, n_mine - b0)
@@ -170,20 +168,30 @@ def infer_one_img(net, img: np.ndarray, config, device: Optional[torch.device] =
         if n_batches == 0:      # more ranks than tiles: still part of the round
             ex.publish(0, 0, 0, first=True, last=True)
         ex.wait(0)
-    kp_d, road_d = fuse_masks_device(scores_all[:n_tiles], tiles, H, W)
+    j.kp_d, j.road_d = fuse_masks_device(scores_all[:n_tiles], tiles, H, W)
     # the masks are return values: start their download now, it overlaps the graph stage
-    kp_h, road_h = _pinned_masks(H, W)
-    kp_h.copy_(kp_d, non_blocking=True)
-    road_h.copy_(road_d, non_blocking=True)
-    masks_done = torch.cuda.Event()
-    masks_done.record()
+    j.kp_h, j.road_h = _pinned_masks(H, W, slot)
+    j.kp_h.copy_(j.kp_d, non_blocking=True)
+    j.road_h.copy_(j.road_d, non_blocking=True)
+    j.masks_done = torch.cuda.Event()
+    j.masks_done.record()
+    return j
+
+
+def _scene_finish(j: _SceneJob, nms_tie_order: Optional[str], timings: Optional[dict]):
+    """Second half of infer_one_img (inferencer.py:112-234) on the current stream: keypoints, pair
+    queries, TopoNet on the stored features, edge aggregation, downloads."""
+    import torch.distributed as dist
+    device, net, config, world, rank, group = j.device, j.net, j.config, j.world, j.rank, j.group
+    n_tiles, tile_xy, P, bs, lo, feats, scene_call = j.n_tiles, j.tile_xy, j.P, j.bs, j.lo, j.feats, j.scene_call
+    kp_h, road_h, masks_done, t_start = j.kp_h, j.road_h, j.masks_done, j.t_start
     if timings is not None:
         torch.cuda.synchronize(device)
     t_pass1 = time.perf_counter()
 
     # ---- keypoints (device) ------------------------------------------------------------------------------
     gx = _scene_graph(device)
-    points_d = gx.extract_graph_points(kp_d, road_d, _cfg_get(config, "ITSC_THRESHOLD"),
+    points_d = gx.extract_graph_points(j.kp_d, j.road_d, _cfg_get(config, "ITSC_THRESHOLD"),
                                        _cfg_get(config, "ROAD_THRESHOLD"),
                                        _cfg_get(config, "ITSC_NMS_RADIUS"),
                                        _cfg_get(config, "ROAD_NMS_RADIUS"), tie_order=nms_tie_order)
@@ -201,6 +209,7 @@ def infer_one_img(net, img: np.ndarray, config, device: Optional[torch.device] =
     # ---- pass 2: TopoNet on the stored features -------------------------------------------------------
     K = int(_cfg_get(config, "MAX_NEIGHBOR_QUERIES"))
     R = float(_cfg_get(config, "NEIGHBOR_RADIUS"))
+
     def _mark():
         if timings is not None:
             torch.cuda.synchronize(device)
@@ -248,6 +257,81 @@ def infer_one_img(net, img: np.ndarray, config, device: Optional[torch.device] =
                        graph_stats=dict(gx.stats),
                        topo_samples=int(sum(nb * nm for (_, _, nb), nm in zip(plan, batch_nmax))))
     return pred_nodes, pred_edges, kp_h.numpy().copy(), road_h.numpy().copy()
+
+
+def _resolve_device(net, device) -> torch.device:
+    if device is None:
+        device = next(net.parameters()).device
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError(f"sam_road_b200 scene inference runs on CUDA only, got '{device}'")
+    return device
+
+
+def infer_one_img(net, img: np.ndarray, config, device: Optional[torch.device] = None,
+                  group=None, timings: Optional[dict] = None, shard: bool = True,
+                  nms_tie_order: Optional[str] = None):
+    """Whole-scene inference (inferencer.py:61-234).
+
+    img: uint8 [H,W,3] RGB.  Returns (pred_nodes int64 [N,2] (r,c), pred_edges int64 [E,2],
+    fused_keypoint_mask uint8 [H,W], fused_road_mask uint8 [H,W]) -- identical on every rank when run
+    distributed.  `shard=False` makes a rank process the whole scene alone even if torch.distributed
+    is up.  `nms_tie_order`: "numpy" (default; this host's np.argsort decides ties like the reference)
+    or "stable" (device-only sort), see sam_road_b200.graph."""
+    device = _resolve_device(net, device)
+    job = _scene_start(net, img, config, device, group, shard)
+    return _scene_finish(job, nms_tie_order, timings)
+
+
+def infer_scenes(net, images, config, device: Optional[torch.device] = None,
+                 nms_tie_order: Optional[str] = None, prefetch: int = 2):
+    """Generator over `infer_one_img(net, img, config)` for a sequence of scenes, as a streaming pipeline
+    (the reference loops `for img_id in test_img_indices` one scene at a time,
+    inferencer.py:271-281): a background thread pulls (reads / decodes) the next images from the `images`
+    iterable while the GPU works, and pass 1 of scene i+1 is enqueued on a second stream BEFORE the graph
+    stage of scene i runs, so the host-side waits of that stage (count read-backs, NumPy's argsort in the
+    default tie-order mode) are covered by encoder work.  Results are identical to infer_one_img's, in
+    order.  Single process / single GPU (the distributed scene path shards ONE scene over the ranks)."""
+    import queue
+    import threading
+    device = _resolve_device(net, device)
+    q: "queue.Queue" = queue.Queue(maxsize=max(1, prefetch))
+    _END = object()
+
+    def _loader():
+        try:
+            for im in images:
+                q.put(im)
+            q.put(_END)
+        except BaseException as e:      # surface loader errors in the consumer
+            q.put(e)
+
+    th = threading.Thread(target=_loader, daemon=True)
+    th.start()
+    streams = [torch.cuda.Stream(device), torch.cuda.Stream(device)]
+    for st in streams:
+        st.wait_stream(torch.cuda.current_stream(device))
+    prev, prev_stream, enc_done, idx = None, None, None, 0
+    while True:
+        item = q.get()
+        if isinstance(item, BaseException):
+            raise item
+        if item is _END:
+            break
+        st = streams[idx % 2]
+        with torch.cuda.stream(st):
+            if enc_done is not None:
+                st.wait_event(enc_done)          # the encoder's activation workspace is shared by the scenes
+            job = _scene_start(net, item, config, device, None, False, slot=idx % 2)
+            enc_done = torch.cuda.Event()
+            enc_done.record(st)
+        if prev is not None:
+            with torch.cuda.stream(prev_stream):
+                yield _scene_finish(prev, nms_tie_order, None)
+        prev, prev_stream, idx = job, st, idx + 1
+    if prev is not None:
+        with torch.cuda.stream(prev_stream):
+            yield _scene_finish(prev, nms_tie_order, None)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -309,13 +393,19 @@ def main(argv=None):
         "./save/infer_" + time.strftime("%Y%m%d_%H%M%S")
     for sub in ("mask", "viz", "graph"):
         os.makedirs(os.path.join(out_dir, sub), exist_ok=True)
-    total = 0.0
-    for img_id in test_ids:
+    loaded = {}
+
+    def read_all():      # runs on infer_scenes' loader thread: decoding overlaps the GPU work of earlier scenes
+        for i in test_ids:
+            im = cv2.cvtColor(cv2.imread(rgb_pattern.format(i)), cv2.COLOR_BGR2RGB)
+            loaded[i] = im
+            yield im
+
+    t0 = time.time()
+    results = infer_scenes(net, read_all(), config, device=device)
+    for img_id, (nodes, edges, itsc_mask, road_mask) in zip(test_ids, results):
         print(f"Processing {img_id}")
-        img = cv2.cvtColor(cv2.imread(rgb_pattern.format(img_id)), cv2.COLOR_BGR2RGB)
-        t0 = time.time()
-        nodes, edges, itsc_mask, road_mask = infer_one_img(net, img, config, device=device)
-        total += time.time() - t0
+        img = loaded.pop(img_id)
         cv2.imwrite(os.path.join(out_dir, "mask", f"{img_id}_road.png"), road_mask)
         cv2.imwrite(os.path.join(out_dir, "mask", f"{img_id}_itsc.png"), itsc_mask)
         viz = cv2.cvtColor(img.copy(), cv2.COLOR_RGB2BGR)
@@ -330,6 +420,7 @@ def main(argv=None):
         with open(os.path.join(out_dir, "graph", f"{img_id}.p"), "wb") as f:
             pickle.dump(convert_to_sat2graph_format(nodes, np.asarray(edges).reshape(-1, 2)), f)
         print(f"Done for {img_id}.")
+    total = time.time() - t0      # wall time of the whole (pipelined) loop, output writing included
     msg = f"Inference completed for {args.config} in {total} seconds."
     print(msg)
     with open(os.path.join(out_dir, "inference_time.txt"), "w") as f:

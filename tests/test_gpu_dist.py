@@ -63,7 +63,7 @@ def test_sharded_scene_equals_single_gpu(world, tmp_path):
     for p in procs:
         p.start()
     for p in procs:
-        p.join(timeout=600)
+        p.join(timeout=240)
         assert p.exitcode == 0
     ok, same, n_nodes, n_edges = open(os.path.join(str(tmp_path), "result.txt")).read().split()
     assert ok == "1" and same == "1", (ok, same, n_nodes, n_edges)

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 from oracle import samroad_oracle as O  # noqa: E402
 from sam_road_b200 import SAMRoad, synth  # noqa: E402
-from sam_road_b200.inferencer import fuse_masks_device, get_patch_info_one_img, infer_one_img  # noqa: E402
+from sam_road_b200.inferencer import fuse_masks_device, get_patch_info_one_img, infer_one_img, infer_scenes  # noqa: E402
 
 DEV = "cuda:0"
 
@@ -135,3 +135,32 @@ def test_scene_with_empty_tiles_and_no_keypoints():
     timings, cfg2 = _check_scene(cfg, img, seed=13, gain=6.0, cand_frac=(2e-6, 8e-6), tie="numpy", min_points=4,
                                  require_edges=False)
     assert timings["n_points"] < 64        # fewer points than tiles: empty tiles are certain
+
+
+def test_infer_scenes_pipeline_equals_sequential():
+    """The streaming multi-scene driver (next scene's pass 1 enqueued on a second stream before the
+    previous scene's graph stage, images pulled by a loader thread) returns exactly what infer_one_img
+    returns scene by scene, in order -- scenes of different content AND different size."""
+    cfg = dict(_scene_cfg(256, 4, 0), INFER_BATCH_SIZE=16, ITSC_THRESHOLD=0.53, ROAD_THRESHOLD=0.5)
+    sd = synth.make_state_dict(cfg, seed=7, logit_gain=6.0)
+    net = SAMRoad(cfg)
+    net.load_state_dict(sd, strict=True)
+    net.eval().to(DEV)
+    rng = np.random.RandomState(9)
+    imgs = [rng.randint(0, 256, size=(sz, sz, 3)).astype(np.uint8) for sz in (400, 400, 512, 400, 300)]
+    seq = [infer_one_img(net, im, cfg, device=torch.device(DEV)) for im in imgs]
+
+    def gen():
+        for im in imgs:
+            yield im
+    pipe = list(infer_scenes(net, gen(), cfg, device=torch.device(DEV)))
+    assert len(pipe) == len(seq)
+    for a, b in zip(seq, pipe):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    assert sum(r[0].shape[0] for r in seq) > 50
+    with pytest.raises(RuntimeError):          # loader errors surface in the consumer
+        def bad():
+            yield imgs[0]
+            raise RuntimeError("decode failed")
+        list(infer_scenes(net, bad(), cfg, device=torch.device(DEV)))
