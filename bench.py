@@ -283,7 +283,7 @@ def run_scenes(args, w, wl, dev, rank, world, barrier):
     import torch
     import torch.distributed as dist
     from sam_road_b200 import SAMRoad, synth
-    from sam_road_b200.inferencer import infer_one_img, infer_scenes
+    from sam_road_b200.inferencer import infer_one_img
     out = {}
     for sc in SCENES.get(wl, []):
         cfg = dict(w["cfg"], SAMPLE_MARGIN=sc["margin"], INFER_PATCHES_PER_EDGE=sc["per_edge"], **SCENE_KEYS,
@@ -320,17 +320,6 @@ def run_scenes(args, w, wl, dev, rank, world, barrier):
                         "stages_ms": {k: round(1e3 * v, 3) for k, v in tm.items() if k.endswith("_s")},
                         "graph_stats": {k: v for k, v in tm.get("graph_stats", {}).items()},
                         "topo_samples": tm.get("topo_samples")}
-        if world == 1:      # a stream of scenes through the pipelined driver (scene i+1's pass 1 under scene i's graph stage)
-            nsc = 2 * args.scene_runs
-            for tie in ("numpy", "stable"):
-                list(infer_scenes(net, [img] * 2, cfg, device=dev, nms_tie_order=tie))          # warm-up
-                torch.cuda.synchronize(dev)
-                t0 = time.perf_counter()
-                outs = list(infer_scenes(net, (img for _ in range(nsc)), cfg, device=dev, nms_tie_order=tie))
-                sec = time.perf_counter() - t0
-                assert len(outs) == nsc
-                res[tie]["pipelined"] = {"value": nsc * n_tiles / sec, "ms_per_scene": 1e3 * sec / nsc, "scenes": nsc,
-                                         "call": "infer_scenes (two streams, loader thread)"}
         res["value"] = res["numpy"]["value"]
         res["note"] = ("'numpy': this host's np.argsort decides the visiting order of equal scores in the greedy "
                        "NMS (bit-exact with the reference on this host); 'stable': device-only sort")

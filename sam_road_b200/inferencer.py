@@ -285,13 +285,15 @@ def infer_one_img(net, img: np.ndarray, config, device: Optional[torch.device] =
 
 def infer_scenes(net, images, config, device: Optional[torch.device] = None,
                  nms_tie_order: Optional[str] = None, prefetch: int = 2):
-    """Generator over `infer_one_img(net, img, config)` for a sequence of scenes, as a streaming pipeline
-    (the reference loops `for img_id in test_img_indices` one scene at a time,
-    inferencer.py:271-281): a background thread pulls (reads / decodes) the next images from the `images`
-    iterable while the GPU works, and pass 1 of scene i+1 is enqueued on a second stream BEFORE the graph
-    stage of scene i runs, so the host-side waits of that stage (count read-backs, NumPy's argsort in the
-    default tie-order mode) are covered by encoder work.  Results are identical to infer_one_img's, in
-    order.  Single process / single GPU (the distributed scene path shards ONE scene over the ranks)."""
+    """Generator over `infer_one_img(net, img, config)` for a sequence of scenes (the reference loops
+    `for img_id in test_img_indices` and reads each image right before it is needed, inferencer.py:271-281):
+    a background thread pulls the next images from the `images` iterable -- file reads and PNG decoding in the
+    CLI -- while the GPU works on the current scene.  Results are infer_one_img's, in order.
+
+    The scenes themselves run back to back on one stream.  Enqueueing the next scene's encoder pass on a second
+    stream under the current scene's graph stage was measured and is NOT done: the encoder kernels are
+    persistent (they hold every SM for 0.2-0.5 ms at a time), so the ~60 small kernels and the read-backs of
+    the graph stage queue behind them, and a C2 scene went from 86.5 to 96.4 ms."""
     import queue
     import threading
     device = _resolve_device(net, device)
@@ -306,32 +308,14 @@ def infer_scenes(net, images, config, device: Optional[torch.device] = None,
         except BaseException as e:      # surface loader errors in the consumer
             q.put(e)
 
-    th = threading.Thread(target=_loader, daemon=True)
-    th.start()
-    streams = [torch.cuda.Stream(device), torch.cuda.Stream(device)]
-    for st in streams:
-        st.wait_stream(torch.cuda.current_stream(device))
-    prev, prev_stream, enc_done, idx = None, None, None, 0
+    threading.Thread(target=_loader, daemon=True).start()
     while True:
         item = q.get()
         if isinstance(item, BaseException):
             raise item
         if item is _END:
-            break
-        st = streams[idx % 2]
-        with torch.cuda.stream(st):
-            if enc_done is not None:
-                st.wait_event(enc_done)          # the encoder's activation workspace is shared by the scenes
-            job = _scene_start(net, item, config, device, None, False, slot=idx % 2)
-            enc_done = torch.cuda.Event()
-            enc_done.record(st)
-        if prev is not None:
-            with torch.cuda.stream(prev_stream):
-                yield _scene_finish(prev, nms_tie_order, None)
-        prev, prev_stream, idx = job, st, idx + 1
-    if prev is not None:
-        with torch.cuda.stream(prev_stream):
-            yield _scene_finish(prev, nms_tie_order, None)
+            return
+        yield infer_one_img(net, item, config, device=device, shard=False, nms_tie_order=nms_tie_order)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -125,6 +125,17 @@ def test_infer_one_img_baseline_grids(name, size, patch, per_edge, margin, cand,
     json.dump(old, open(path, "w"), indent=1, sort_keys=True, default=str)
 
 
+def test_scene_with_dense_candidates():
+    """Thresholds that let 30 % / 60 % of the pixels through (what the reference's default thresholds do on an
+    untrained model): every candidate has hundreds of candidates inside its NMS disc."""
+    rng = np.random.RandomState(8)
+    img = rng.randint(0, 256, size=(400, 400, 3)).astype(np.uint8)
+    for tie in ("numpy", "stable"):
+        timings, _ = _check_scene(dict(_scene_cfg(256, 4, 0), INFER_BATCH_SIZE=16), img, seed=9, gain=6.0,
+                                  cand_frac=(0.3, 0.6), tie=tie, min_points=100)
+        assert sum(timings["graph_stats"]["candidates"]) > 100000
+
+
 def test_scene_with_empty_tiles_and_no_keypoints():
     """C4 grid with thresholds so high that only a handful of keypoints survive: most tiles hold no
     point (zero-row queries inside a non-empty batch), and with thresholds nothing passes the early
@@ -138,9 +149,8 @@ def test_scene_with_empty_tiles_and_no_keypoints():
 
 
 def test_infer_scenes_pipeline_equals_sequential():
-    """The streaming multi-scene driver (next scene's pass 1 enqueued on a second stream before the
-    previous scene's graph stage, images pulled by a loader thread) returns exactly what infer_one_img
-    returns scene by scene, in order -- scenes of different content AND different size."""
+    """The multi-scene driver (images pulled by a loader thread while the GPU works) returns exactly what
+    infer_one_img returns scene by scene, in order -- scenes of different content AND different size."""
     cfg = dict(_scene_cfg(256, 4, 0), INFER_BATCH_SIZE=16, ITSC_THRESHOLD=0.53, ROAD_THRESHOLD=0.5)
     sd = synth.make_state_dict(cfg, seed=7, logit_gain=6.0)
     net = SAMRoad(cfg)
