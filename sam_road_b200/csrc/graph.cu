@@ -333,11 +333,11 @@ __global__ void gather_sorted3_kernel(const int32_t* __restrict__ cand3, const i
 // One round: every undecided pixel looks at its disc; a kept pixel of lower rank suppresses it, an
 // undecided one of lower rank makes it wait, otherwise it is kept.  Decisions only ever use final
 // states of lower ranks, so the fixed point is the sequential greedy result whatever the schedule.
-// A CTA owns a 32x32 pixel tile, stages tile + halo in shared memory (odd row stride: the 32 lanes of
+// A CTA owns a 64x64 pixel tile, stages tile + halo in shared memory (odd row stride: the 32 lanes of
 // a warp scan 32 different rows of one disc, conflict-free) and iterates locally until nothing in the
 // tile changes; rounds repeat until no undecided pixel is left in the scene.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kNmsTile = 32;
+constexpr int kNmsTile = 64;       // pixels per CTA tile side (fewer cross-tile rounds than 32; 37 KB of smem at halo 16)
 constexpr int kNmsMaxHalo = 32;
 
 __global__ void cell_build_kernel(const int32_t* __restrict__ sorted_pix, const uint8_t* __restrict__ immune,
@@ -358,7 +358,7 @@ nms_round_kernel(uint32_t* __restrict__ cell, int H, int W, int halo, int d2max,
   const int SH = kNmsTile + 2 * halo;
   volatile uint32_t* s = smem_u32_;               // [SH][S]
   int* wtab = reinterpret_cast<int*>(smem_u32_ + SH * S);         // [2*halo+1] half-widths
-  unsigned short* list = reinterpret_cast<unsigned short*>(wtab + 2 * halo + 1);   // [1024]
+  unsigned short* list = reinterpret_cast<unsigned short*>(wtab + 2 * halo + 1);   // [kNmsTile^2]
   __shared__ int list_n, changed_any;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gx0 = blockIdx.x * kNmsTile - halo, gy0 = blockIdx.y * kNmsTile - halo;
@@ -382,16 +382,17 @@ nms_round_kernel(uint32_t* __restrict__ cell, int H, int W, int halo, int d2max,
   }
   __syncthreads();
 
-  for (int iter = 0; iter < 64; ++iter) {
+  for (int iter = 0; iter < 128; ++iter) {
     if (tid == 0) { list_n = 0; changed_any = 0; }
     __syncthreads();
+    for (int ly = warp; ly < kNmsTile; ly += 8) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int ly = warp + 8 * q, lx = lane;
-      const uint32_t v = s[(ly + halo) * S + lx + halo];
-      if (v != kNone && (v & 3u) == kUndecided) {
-        const int p = atomicAdd(&list_n, 1);
-        list[p] = static_cast<unsigned short>(ly * kNmsTile + lx);
+      for (int lx = lane; lx < kNmsTile; lx += 32) {
+        const uint32_t v = s[(ly + halo) * S + lx + halo];
+        if (v != kNone && (v & 3u) == kUndecided) {
+          const int p = atomicAdd(&list_n, 1);
+          list[p] = static_cast<unsigned short>(ly * kNmsTile + lx);
+        }
       }
     }
     __syncthreads();
@@ -428,14 +429,15 @@ nms_round_kernel(uint32_t* __restrict__ cell, int H, int W, int halo, int d2max,
   }
   // write back the decisions of this tile, count what is still open
   int open = 0;
+  for (int ly = warp; ly < kNmsTile; ly += 8) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int ly = warp + 8 * q, lx = lane;
-    const int gx = blockIdx.x * kNmsTile + lx, gy = blockIdx.y * kNmsTile + ly;
-    const uint32_t v = s[(ly + halo) * S + lx + halo];
-    if (v != kNone && gx < W && gy < H) {
-      if ((v & 3u) == kUndecided) ++open;
-      else cell[static_cast<size_t>(gy) * W + gx] = v;
+    for (int lx = lane; lx < kNmsTile; lx += 32) {
+      const int gx = blockIdx.x * kNmsTile + lx, gy = blockIdx.y * kNmsTile + ly;
+      const uint32_t v = s[(ly + halo) * S + lx + halo];
+      if (v != kNone && gx < W && gy < H) {
+        if ((v & 3u) == kUndecided) ++open;
+        else cell[static_cast<size_t>(gy) * W + gx] = v;
+      }
     }
   }
   for (int o = 16; o > 0; o >>= 1) open += __shfl_xor_sync(0xffffffffu, open, o);
@@ -542,7 +544,7 @@ int nms_pass(samroad_graph_ctx* g, const int32_t* sorted_pix, const uint8_t* imm
   SRB_CUDA_OK(cudaMemsetAsync(g->tile_und.p, 0x01, sizeof(int) * tx * ty, st));
   const bool tiled = halo <= kNmsMaxHalo;
   const int SH = kNmsTile + 2 * halo;
-  const size_t smem = tiled ? (static_cast<size_t>(SH) * (SH + 1) + 2 * halo + 1) * 4 + 1024 * 2 : 0;
+  const size_t smem = tiled ? (static_cast<size_t>(SH) * (SH + 1) + 2 * halo + 1) * 4 + kNmsTile * kNmsTile * 2 : 0;
   if (tiled && smem > 48 * 1024)
     SRB_CUDA_OK(cudaFuncSetAttribute(nms_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(smem)));

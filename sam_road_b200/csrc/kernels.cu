@@ -237,20 +237,54 @@ __global__ void __launch_bounds__(256)
 fuse_masks_kernel(const float* __restrict__ scores, int n_tiles, int P,
                   const int* __restrict__ tx0, const int* __restrict__ ty0, int H, int W,
                   uint8_t* __restrict__ kp, uint8_t* __restrict__ road) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  // the CTA owns 256 consecutive pixels of one scene row; it first lists (in tile-list order) the tiles that
+  // touch that segment at all, so that a pixel walks a few dozen candidates instead of every tile of the scene
+  __shared__ int s_list[1024];
+  __shared__ int s_n;
+  __shared__ int sw[33];
+  const int xb = blockIdx.x * blockDim.x;
+  const int x = xb + threadIdx.x;
   const int y = blockIdx.y;
-  if (x >= W || y >= H) return;
   float a0 = 0.f, a1 = 0.f, cnt = 0.f;
-  for (int t = 0; t < n_tiles; ++t) {
-    const int lx = x - __ldg(tx0 + t), ly = y - __ldg(ty0 + t);
-    if (lx >= 0 && lx < P && ly >= 0 && ly < P) {
-      const float2 sc = *reinterpret_cast<const float2*>(
-          scores + ((static_cast<size_t>(t) * P + ly) * P + lx) * 2);
-      a0 = __fadd_rn(a0, sc.x);
-      a1 = __fadd_rn(a1, sc.y);
-      cnt = __fadd_rn(cnt, 1.0f);
+  for (int t0 = 0; t0 < n_tiles; t0 += 1024) {       // chunks of 1024 tiles keep the list in shared memory
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (int b = 0; b < 1024; b += 256) {
+      const int t = t0 + b + threadIdx.x;
+      bool hit = false;
+      if (t < n_tiles) {
+        const int ox = __ldg(tx0 + t), oy = __ldg(ty0 + t);
+        hit = y >= oy && y < oy + P && ox < xb + 256 && ox + P > xb;
+      }
+      // ordered append: exclusive scan of the hit flags over the block
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+      if (lane == 0) sw[wid] = __popc(bal);
+      __syncthreads();
+      int base = s_n;
+      for (int w = 0; w < wid; ++w) base += sw[w];
+      if (hit) s_list[base + __popc(bal & ((1u << lane) - 1u))] = t;
+      __syncthreads();
+      if (threadIdx.x == 0) { int tot = 0; for (int w = 0; w < 8; ++w) tot += sw[w]; s_n += tot; }
+      __syncthreads();
     }
+    const int n = s_n;
+    if (x < W) {
+      for (int i = 0; i < n; ++i) {
+        const int t = s_list[i];
+        const int lx = x - __ldg(tx0 + t), ly = y - __ldg(ty0 + t);
+        if (lx >= 0 && lx < P) {
+          const float2 sc = *reinterpret_cast<const float2*>(
+              scores + ((static_cast<size_t>(t) * P + ly) * P + lx) * 2);
+          a0 = __fadd_rn(a0, sc.x);
+          a1 = __fadd_rn(a1, sc.y);
+          cnt = __fadd_rn(cnt, 1.0f);
+        }
+      }
+    }
+    __syncthreads();
   }
+  if (x >= W) return;
   uint8_t o0 = 0, o1 = 0;
   if (cnt > 0.f) {
     const float f0 = __fmul_rn(__fdiv_rn(a0, cnt), 255.0f);
