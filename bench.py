@@ -438,7 +438,8 @@ def run_native(args, w, wl):
     h_tiles = [t.cpu().pin_memory() for t in tiles]
     h_topo = [[t.contiguous().pin_memory() for t in (th[0], th[1], th[2].view(torch.uint8))]
               for th in topo_host] if NP else None
-    exchange_backend = (ex_sc.backend + (f" ({ex_sc.note})" if ex_sc.note else "")) if ex_sc is not None else None
+    exchange_backend = (f"{ex_sc.backend}, barrier: {getattr(ex_sc, 'barrier_kind', 'n/a')}" +
+                        (f" ({ex_sc.note})" if ex_sc.note else "")) if ex_sc is not None else None
     del tiles, topo                                      # the e2e leg owns its own (staged) device buffers
     ex_sc = ex_ts = None
     torch.cuda.empty_cache()

@@ -185,6 +185,13 @@ int samroad_infer_batch_host_async(samroad_handle_t h, int slot, const void* rgb
                                    float* image_embeddings_host, float* topo_scores_host);
 int samroad_infer_batch_host_wait(samroad_handle_t h, int slot);
 
+/* Stream memory operations on a 32-bit flag word in device (or peer-mapped) memory, executed by the stream
+ * front end without a kernel: an ordered write of `value`, and a wait until *addr >= value.  The exchange step
+ * between ranks (sam_road_b200/exchange.py; no reference counterpart, the reference is single-GPU) builds its
+ * barrier from them so that no SM spins beside the persistent compute kernels. */
+int samroad_stream_write_value32(void* addr, uint32_t value, void* stream);
+int samroad_stream_wait_value32(void* addr, uint32_t value, void* stream);
+
 /* Per-kernel-class CUDA-event timing on the launching stream (bench.py's roofline numbers).
  * samroad_timing_enable(h, 1) clears and starts recording; samroad_timing_read() synchronises and
  * writes a JSON object {"<class>": {"launches","ms","flops","bytes"}, ...} into buf. */

@@ -60,6 +60,8 @@ SIGNATURES = {
     "samroad_infer_batch_host_async": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _vp,
                                             _vp]),
     "samroad_infer_batch_host_wait": (_i, [_vp, _i]),
+    "samroad_stream_write_value32": (_i, [_vp, C.c_uint32, _vp]),
+    "samroad_stream_wait_value32": (_i, [_vp, C.c_uint32, _vp]),
     "samroad_timing_enable": (_i, [_vp, _i]),
     "samroad_timing_read": (_i, [_vp, C.c_char_p, C.c_size_t]),
     "samroad_workspace_bytes": (C.c_size_t, [_vp, _i]),

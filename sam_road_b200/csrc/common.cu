@@ -148,6 +148,32 @@ int make_tmap_f32_4d_dense(CUtensorMap* out, const void* base, const uint64_t di
   return 0;
 }
 
+// Stream memory operations (cuStreamWriteValue32 / cuStreamWaitValue32): flag writes and waits executed by the
+// stream front end, no kernel and no SM involved -- the exchange step's barrier between ranks uses them on
+// symmetric (peer-mapped) flag words so that nothing spins on an SM next to the persistent compute kernels.
+typedef CUresult (*PFN_streamMemOp32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static PFN_streamMemOp32 get_memop_fn(const char* name) {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+    return reinterpret_cast<PFN_streamMemOp32>(p);
+  return nullptr;
+}
+int stream_write_value32(void* addr, uint32_t value, cudaStream_t st) {
+  static PFN_streamMemOp32 fn = get_memop_fn("cuStreamWriteValue32");
+  SRB_REQUIRE(fn != nullptr, "cuStreamWriteValue32 driver entry point not available");
+  const CUresult r = fn(reinterpret_cast<CUstream>(st), reinterpret_cast<CUdeviceptr>(addr), value, 0 /* default: ordered write */);
+  SRB_REQUIRE(r == CUDA_SUCCESS, "cuStreamWriteValue32 failed (%d)", static_cast<int>(r));
+  return 0;
+}
+int stream_wait_value32_geq(void* addr, uint32_t value, cudaStream_t st) {
+  static PFN_streamMemOp32 fn = get_memop_fn("cuStreamWaitValue32");
+  SRB_REQUIRE(fn != nullptr, "cuStreamWaitValue32 driver entry point not available");
+  const CUresult r = fn(reinterpret_cast<CUstream>(st), reinterpret_cast<CUdeviceptr>(addr), value, CU_STREAM_WAIT_VALUE_GEQ);
+  SRB_REQUIRE(r == CUDA_SUCCESS, "cuStreamWaitValue32 failed (%d)", static_cast<int>(r));
+  return 0;
+}
+
 // Traversal direction of the next row-streaming kernel (LayerNorm, 2-CTA GEMMs, encoder attention):
 // the encoder alternates it from kernel to kernel so that each kernel starts on the rows its
 // producer wrote last, i.e. on what is still in the 126 MB L2 (activations are 100-400 MB).

@@ -1081,6 +1081,12 @@ extern "C" int samroad_infer_batch_host(samroad_handle_t h, const void* rgb_host
   return samroad_infer_batch_host_wait(h, 0);
 }
 
+extern "C" int samroad_stream_write_value32(void* addr, uint32_t value, void* stream) {
+  return stream_write_value32(addr, value, static_cast<cudaStream_t>(stream));
+}
+extern "C" int samroad_stream_wait_value32(void* addr, uint32_t value, void* stream) {
+  return stream_wait_value32_geq(addr, value, static_cast<cudaStream_t>(stream));
+}
 extern "C" uint64_t samroad_launch_count(int reset) { return launch_count(reset != 0); }
 extern "C" const char* samroad_last_error(void) { return get_last_error(); }
 extern "C" int samroad_abi_version(void) { return SAMROAD_ABI_VERSION; }

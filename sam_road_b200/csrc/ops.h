@@ -25,6 +25,9 @@ int device_sm_count();
 // true the first time it is called with this mask on the current CUDA device (then sets the bit)
 bool first_use_on_device(uint64_t* device_mask);
 void note_launch(int n = 1);
+// stream memory operations on a 32-bit flag word (no kernel): ordered write / wait until *addr >= value
+int stream_write_value32(void* addr, uint32_t value, cudaStream_t st);
+int stream_wait_value32_geq(void* addr, uint32_t value, cudaStream_t st);
 uint64_t launch_count(bool reset);
 
 // ---- GEMM family (gemm_ops.cu) : C = A[M,K] * W[N,K]^T with fused epilogues ------------------------

@@ -34,6 +34,8 @@ class TileExchange:
         self.backend = "nccl_async"
         self.note = ""
         self._bufs, self._hdl, self._peer = [], [], []
+        self._flags = self._flag_peers = None      # symmetric int32 [slots, world] + peer views (memop barrier)
+        self._round = [0] * slots
         self._works = [None] * slots
         self._done = [None] * slots
         self.stream = torch.cuda.Stream(self.device)
@@ -48,12 +50,50 @@ class TileExchange:
                     self._hdl.append(hdl)
                     self._peer.append([buf if r == self.rank else hdl.get_buffer(r, full, dtype)
                                        for r in range(self.world)])
+                flags = symm_mem.empty((slots, self.world), dtype=torch.int32, device=self.device)
+                flags.zero_()
+                fh = symm_mem.rendezvous(flags, grp)
+                self._flags, self._flag_hdl = flags, fh
+                self._flag_peers = [flags if r == self.rank else fh.get_buffer(r, (slots, self.world), torch.int32)
+                                    for r in range(self.world)]
+                torch.cuda.synchronize(self.device)
+                dist.barrier(group=group)              # every rank's flags are zero before anybody writes
                 self.backend = "peer_copy_engine"
+                try:                                   # probe the stream memory operations once
+                    self._barrier_memops(0, self.stream)
+                    self.stream.synchronize()
+                    self.barrier_kind = "stream_memops"
+                except Exception as e:
+                    self.barrier_kind = f"signal_pad_kernel ({type(e).__name__})"
+                dist.barrier(group=group)
             except Exception as e:      # symmetric memory unavailable on this system: NCCL path
                 self.note = f"symmetric memory unavailable ({type(e).__name__}: {str(e)[:120]})"
                 self._bufs, self._hdl, self._peer = [], [], []
         if not self._bufs:
             self._bufs = [torch.empty(full, dtype=dtype, device=self.device) for _ in range(slots)]
+
+    def _barrier_memops(self, slot: int, stream) -> None:
+        """Arrive (write the round number into this rank's word of every peer's flag row) and wait (until
+        every word of this rank's own row has reached it) -- stream memory operations, no kernel."""
+        from . import _lib
+        lib = _lib.load()
+        self._round[slot] += 1
+        r = self._round[slot]
+        sp = stream.cuda_stream
+        for k in range(1, self.world):
+            peer = (self.rank + k) % self.world
+            addr = self._flag_peers[peer].data_ptr() + 4 * (slot * self.world + self.rank)
+            _lib.check(lib.samroad_stream_write_value32(addr, r, sp), "samroad_stream_write_value32")
+        for k in range(1, self.world):
+            peer = (self.rank + k) % self.world
+            addr = self._flags.data_ptr() + 4 * (slot * self.world + peer)
+            _lib.check(lib.samroad_stream_wait_value32(addr, r, sp), "samroad_stream_wait_value32")
+
+    def _barrier(self, slot: int) -> None:
+        if getattr(self, "barrier_kind", "") == "stream_memops":
+            self._barrier_memops(slot, self.stream)
+        else:
+            self._hdl[slot].barrier(channel=slot)
 
     # the rank's own block inside its gather buffer: producers write their results straight into it
     def local_block(self, slot: int = 0) -> torch.Tensor:
@@ -76,7 +116,7 @@ class TileExchange:
             with torch.cuda.stream(self.stream):
                 self.stream.wait_event(ready)
                 if first:
-                    self._hdl[slot].barrier(channel=slot)    # every rank is done with the slot's old contents
+                    self._barrier(slot)                      # every rank is done with the slot's old contents
                 if hi > lo:
                     src = self.local_block(slot)[lo:hi]
                     a, b = self.rank * self.rows + lo, self.rank * self.rows + hi
@@ -84,7 +124,7 @@ class TileExchange:
                         peer = (self.rank + r) % self.world
                         self._peer[slot][peer][a:b].copy_(src, non_blocking=True)
                 if last:
-                    self._hdl[slot].barrier(channel=slot)    # all ranks' pushes into this slot have landed
+                    self._barrier(slot)                      # all ranks' pushes into this slot have landed
                     ev = torch.cuda.Event()
                     ev.record()
                     self._done[slot] = ev
