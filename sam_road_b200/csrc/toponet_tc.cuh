@@ -11,12 +11,14 @@
 //   smem  A buffer 32 KB  current fp16 GEMM A operand (x -> attention output -> x' -> hidden -> x'')
 //         KV buffer 66 KB k and v of the tile as fp16 rows
 //         weight ring 3 x 32 KB  the 18 [128x128] weight chunks streamed by TMA in consumption order
-// Warps: 0 = TMA producer, 1 = MMA issuer + TMEM allocator, 2..9 = 256 token threads, TWO per token
-// (warps w and w+4 share a TMEM lane quarter): epilogues, attention on CUDA cores, LayerNorm,
-// output_proj.  Part 0 owns columns 0..63 / heads 0,1 / the k rows, part 1 columns 64..127 / heads 2,3 /
-// the v rows; LayerNorm statistics and the output dot product are combined through a small smem
-// exchange.  The token work, not the GEMMs, bounds this kernel (two warps per scheduler hide twice the
-// latency of one).  Key-padding semantics: masked
+// Warps: 0 = TMA producer, 1 = MMA issuer + TMEM allocator, 2..17 = 512 token threads, FOUR per token
+// (warps w, w+4, w+8, w+12 share a TMEM lane quarter): epilogues, attention on CUDA cores, LayerNorm,
+// output_proj.  Part p owns columns 32p..32p+31 = head p, and two of the eight 32-column chunks of k|v;
+// a thread keeps its 32 columns of the row in registers through a whole LayerNorm (one TMEM read, one
+// write).  LayerNorm statistics and the output dot product are combined through a small smem exchange,
+// always summed in part order.  The token work, not the GEMMs, bounds this kernel, and it is bound by
+// latency (one tile in flight per CTA, phases separated by the MMA round trips): four warps per
+// scheduler hide twice the latency of two (one -> two threads per token was 1.58x in round 1).  Key-padding semantics: masked
 // keys are excluded from the softmax; masked slots report output_proj.bias.
 #pragma once
 
@@ -25,15 +27,16 @@
 
 namespace srb {
 
-constexpr int kTtcThreads = 320;
+constexpr int kTtcThreads = 576;          // 2 + 16 warps
+constexpr int kTtcTokenThreads = 512;
 constexpr int kTtcWStages = 3;
 constexpr int kTtcOffA = 0;                       // 2 k-blocks x 16 KB
 constexpr int kTtcOffKV = 32768;                  // 128 rows x 528 B (k|v fp16, padded) / x fp32 tile
 constexpr int kTtcKVStride = 528;
 constexpr int kTtcOffW = kTtcOffKV + 68608;       // 3 x 32 KB
 constexpr int kTtcOffBar = kTtcOffW + kTtcWStages * 32768;
-constexpr int kTtcOffXch = kTtcOffBar + 256;      // 3 slots x 256 floats: partial sums of the two parts
-constexpr int kTtcSmemBytes = kTtcOffXch + 3 * 1024 + 1024;
+constexpr int kTtcOffXch = kTtcOffBar + 256;      // 3 slots x 4 parts x 128 floats: partial sums of the parts
+constexpr int kTtcSmemBytes = kTtcOffXch + 3 * 2048 + 1024;
 constexpr int kTtcChunksPerLayer = 6;             // Wq, Wk, Wv, Wo, W1, W2
 
 struct TtcLayerParams {
@@ -74,7 +77,7 @@ __device__ __forceinline__ long long ttc_load_index(const void* p, int dtype, si
 }
 
 __device__ __forceinline__ void named_bar_sync_tokens() {
-  asm volatile("bar.sync 1, 256;" ::: "memory");
+  asm volatile("bar.sync 1, 512;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(kTtcThreads, 1)
@@ -86,7 +89,7 @@ toponet_tc_kernel(const __grid_constant__ CUtensorMap tmW, TtcParams p) {
   uint8_t* sKV = smem + kTtcOffKV;
   uint8_t* sW = smem + kTtcOffW;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTtcOffBar);
-  uint64_t* a_ready = bars + 2;     // 256 token threads: new A operand written
+  uint64_t* a_ready = bars + 2;     // 512 token threads: new A operand written
   uint64_t* acc_ready = bars + 3;   // MMA commit: GEMM result in TMEM
   uint64_t* w_full = bars + 4;      // [3]
   uint64_t* w_empty = bars + 7;     // [3]
@@ -97,7 +100,7 @@ toponet_tc_kernel(const __grid_constant__ CUtensorMap tmW, TtcParams p) {
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmW);
-    mbar_init(a_ready, 256);
+    mbar_init(a_ready, kTtcTokenThreads);
     mbar_init(acc_ready, 1);
     for (int i = 0; i < kTtcWStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     fence_barrier_init();
@@ -158,14 +161,14 @@ toponet_tc_kernel(const __grid_constant__ CUtensorMap tmW, TtcParams p) {
   } else {
     // =========================== token threads ===========================
     const int quarter = warp & 3;
-    const int part = (warp - 2) >> 2;                 // 0: columns 0..63, 1: columns 64..127
+    const int part = (warp - 2) >> 2;                 // 0..3: columns 32*part .. 32*part+31, head `part`
     const int row = quarter * 32 + lane;
     const uint32_t tlane = static_cast<uint32_t>(quarter * 32) << 16;
     const uint32_t tAcc = tmem_base + tlane;          // cols [0,384)
     const uint32_t tRes = tmem_base + tlane + 384;    // cols [384,512)
     const int sw = row & 7;
     uint8_t* myA = sA + row * 128;
-    float* xch = reinterpret_cast<float*>(smem + kTtcOffXch);   // [3][2 parts][128 rows]
+    float* xch = reinterpret_cast<float*>(smem + kTtcOffXch);   // [3][4 parts][128 rows]
     int ti = 0, rc = 0;                               // tiles, acc_ready completions consumed
 
     auto write_a_chunk = [&](int c, const float (&v)[32]) {   // 32 fp32 -> fp16 into the swizzled A buffer
@@ -193,59 +196,65 @@ toponet_tc_kernel(const __grid_constant__ CUtensorMap tmW, TtcParams p) {
       for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(v[i]);
       tmem_st_32x32(taddr, r);
     };
-    // this thread's partial + the other part's partial of the same row (slot: 0 sum, 1 var, 2 dot)
+    // the four parts' partials of the same row, summed in part order (slot: 0 sum, 1 var, 2 dot): every
+    // thread of a row gets the same value
     auto combine = [&](int slot, float mine) -> float {
-      xch[slot * 256 + part * 128 + row] = mine;
+      float* x = xch + slot * 512 + row;
+      x[part * 128] = mine;
       named_bar_sync_tokens();
-      return mine + xch[slot * 256 + (part ^ 1) * 128 + row];
+      return ((x[0] + x[128]) + x[256]) + x[384];
+    };
+    auto ldg32 = [&](const float* src, float (&v)[32]) {     // 32 consecutive floats (128 B aligned)
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 t = __ldg(s4 + i);
+        v[4 * i + 0] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+      }
     };
     // x = LayerNorm(res + acc + bias) ; res <- x ; optionally A buffer <- fp16(x); returns x.w_out
-    // (this part's two 32-column chunks; exact two-pass statistics over the whole row)
+    // (this part's 32 columns, held in registers; exact two-pass statistics over the whole row)
     auto residual_layernorm = [&](const float* bias, const float* gamma, const float* beta,
                                   bool write_a, const float* wdot) -> float {
+      const int c = part;
+      float r[32];
       float sum = 0.f;
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = part * 2 + cc;
-        float a[32], r[32];
-        ld_chunk(tAcc + c * 32, a);
-        ld_chunk(tRes + c * 32, r);
+      {
+        uint32_t ua[32], ur[32];
+        tmem_ld_32x32_nowait(tAcc + c * 32, ua);
+        tmem_ld_32x32_nowait(tRes + c * 32, ur);
+        float bv[32];
+        ldg32(bias + c * 32, bv);
+        tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          r[i] += a[i] + __ldg(bias + c * 32 + i);
+          r[i] = __uint_as_float(ur[i]) + (__uint_as_float(ua[i]) + bv[i]);
           sum += r[i];
         }
-        st_chunk(tRes + c * 32, r);
       }
-      tmem_st_wait();
       const float mean = combine(0, sum) * (1.0f / 128.0f);
       float var = 0.f;
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = part * 2 + cc;
-        float r[32];
-        ld_chunk(tRes + c * 32, r);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float d = r[i] - mean;
-          var = fmaf(d, d, var);
-        }
+      for (int i = 0; i < 32; ++i) {
+        const float d = r[i] - mean;
+        var = fmaf(d, d, var);
       }
       const float rstd = rsqrtf(combine(1, var) * (1.0f / 128.0f) + 1e-5f);
       float dot = 0.f;
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = part * 2 + cc;
-        float r[32];
-        ld_chunk(tRes + c * 32, r);
+      {
+        float gv[32], bt[32];
+        ldg32(gamma + c * 32, gv);
+        ldg32(beta + c * 32, bt);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          r[i] = (r[i] - mean) * rstd * __ldg(gamma + c * 32 + i) + __ldg(beta + c * 32 + i);
-          if (wdot) dot = fmaf(r[i], __ldg(wdot + c * 32 + i), dot);
+        for (int i = 0; i < 32; ++i) r[i] = (r[i] - mean) * rstd * gv[i] + bt[i];
+        if (wdot) {
+          ldg32(wdot + c * 32, gv);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) dot = fmaf(r[i], gv[i], dot);
         }
-        st_chunk(tRes + c * 32, r);
-        if (write_a) write_a_chunk(c, r);
       }
+      st_chunk(tRes + c * 32, r);
+      if (write_a) write_a_chunk(c, r);
       tmem_st_wait();
       return dot;
     };
@@ -292,9 +301,8 @@ toponet_tc_kernel(const __grid_constant__ CUtensorMap tmW, TtcParams p) {
         if (ti == 0) pair_lookup(tile);              // later tiles: looked up during the previous tile
         const float ox = nx_ox, oy = nx_oy;
         const size_t ps = nx_ps, pt = nx_pt;
-#pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
-          const int c = part * 2 + cc;
+        {
+          const int c = part;
           float v[32];
           const float4* a4 = reinterpret_cast<const float4*>(p.pst + ps * 256 + c * 32);
           const float4* b4 = reinterpret_cast<const float4*>(p.pst + pt * 256 + 128 + c * 32);
@@ -330,38 +338,44 @@ toponet_tc_kernel(const __grid_constant__ CUtensorMap tmW, TtcParams p) {
         // ================= qkv: k, v -> smem (fp16 rows), attention per head =================
         mbar_wait(acc_ready, rc & 1); ++rc;
         tc_fence_after_sync();
-#pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {              // part 0: k (cols 128..255), part 1: v (cols 256..383)
-          const int c = part * 4 + cc;
-          float v[32];
-          ld_chunk(tAcc + 128 + c * 32, v);
-          uint8_t* dst = sKV + row * kTtcKVStride + ((c * 64) ^ (((row >> 4) & 1) << 6));
+        {                                            // parts 0,1: k (cols 128..255), parts 2,3: v (cols 256..383)
+          uint32_t kv[2][32];
+          tmem_ld_32x32_nowait(tAcc + 128 + (part * 2 + 0) * 32, kv[0]);
+          tmem_ld_32x32_nowait(tAcc + 128 + (part * 2 + 1) * 32, kv[1]);
+          tmem_ld_wait();
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            uint4 u;
-            const float* b = L.in_b + 128 + c * 32 + q4 * 8;
-            u.x = pack_half2(v[q4 * 8 + 0] + __ldg(b + 0), v[q4 * 8 + 1] + __ldg(b + 1));
-            u.y = pack_half2(v[q4 * 8 + 2] + __ldg(b + 2), v[q4 * 8 + 3] + __ldg(b + 3));
-            u.z = pack_half2(v[q4 * 8 + 4] + __ldg(b + 4), v[q4 * 8 + 5] + __ldg(b + 5));
-            u.w = pack_half2(v[q4 * 8 + 6] + __ldg(b + 6), v[q4 * 8 + 7] + __ldg(b + 7));
-            *reinterpret_cast<uint4*>(dst + q4 * 16) = u;
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c = part * 2 + cc;
+            uint8_t* dst = sKV + row * kTtcKVStride + ((c * 64) ^ (((row >> 4) & 1) << 6));
+            const float4* b4 = reinterpret_cast<const float4*>(L.in_b + 128 + c * 32);
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const float4 b0 = __ldg(b4 + 2 * q4), b1 = __ldg(b4 + 2 * q4 + 1);
+              const uint32_t* v = kv[cc] + q4 * 8;
+              uint4 u;
+              u.x = pack_half2(__uint_as_float(v[0]) + b0.x, __uint_as_float(v[1]) + b0.y);
+              u.y = pack_half2(__uint_as_float(v[2]) + b0.z, __uint_as_float(v[3]) + b0.w);
+              u.z = pack_half2(__uint_as_float(v[4]) + b1.x, __uint_as_float(v[5]) + b1.y);
+              u.w = pack_half2(__uint_as_float(v[6]) + b1.z, __uint_as_float(v[7]) + b1.w);
+              *reinterpret_cast<uint4*>(dst + q4 * 16) = u;
+            }
           }
         }
-        named_bar_sync_tokens();
         const uint8_t* kv0 = sKV + (row & ~15) * kTtcKVStride;   // first token of this sample
         const int sx = ((row >> 4) & 1) << 6;                    // odd samples: columns XOR 64 B
-#pragma unroll 1
-        for (int hh2 = 0; hh2 < 2; ++hh2) {
-          const int h = part * 2 + hh2;
+        {
+          const int h = part;
           float2 q2[16];
           {
-            float q[32];
-            ld_chunk(tAcc + h * 32, q);
+            uint32_t q[32];
+            tmem_ld_32x32_nowait(tAcc + h * 32, q);  // in flight across the barrier
+            named_bar_sync_tokens();                 // the sample's k and v rows are in smem
+            tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 16; ++i) {   // torch MHA scales q by 1/sqrt(head_dim)
               const float2 bb = __ldg(reinterpret_cast<const float2*>(L.in_b + h * 32) + i);
-              q2[i] = make_float2((q[2 * i] + bb.x) * 0.17677669529663687f,
-                                  (q[2 * i + 1] + bb.y) * 0.17677669529663687f);
+              q2[i] = make_float2((__uint_as_float(q[2 * i]) + bb.x) * 0.17677669529663687f,
+                                  (__uint_as_float(q[2 * i + 1]) + bb.y) * 0.17677669529663687f);
             }
           }
           float sc[16];
@@ -417,13 +431,13 @@ toponet_tc_kernel(const __grid_constant__ CUtensorMap tmW, TtcParams p) {
         // ================= linear1 + relu =================
         mbar_wait(acc_ready, rc & 1); ++rc;
         tc_fence_after_sync();
-#pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
-          const int c = part * 2 + cc;
-          float v[32];
+        {
+          const int c = part;
+          float v[32], bv[32];
+          ldg32(L.l1_b + c * 32, bv);
           ld_chunk(tAcc + c * 32, v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + __ldg(L.l1_b + c * 32 + i), 0.f);
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bv[i], 0.f);
           write_a_chunk(c, v);
         }
         tc_fence_before_sync();
