@@ -76,11 +76,28 @@ __device__ __forceinline__ long long ttc_load_index(const void* p, int dtype, si
   return static_cast<long long>(static_cast<const int*>(p)[idx]);
 }
 
+// warp-level MMA for the 16 x 16 attention of one sample and head (far too small for a UMMA tile)
+__device__ __forceinline__ void ttc_ldmatrix_x4(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr) : "memory");
+}
+__device__ __forceinline__ void ttc_ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr) : "memory");
+}
+// d (16x8, fp32) += a (16x16, fp16, row) * b (16x8, fp16, col)
+__device__ __forceinline__ void ttc_mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+               "{%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 __device__ __forceinline__ void named_bar_sync_tokens() {
   asm volatile("bar.sync 1, 512;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(kTtcThreads, 1)
+__global__ void __launch_bounds__(kTtcThreads, 1)   // 18 warps: 5 on two of the sub-partitions -> 96 registers
 toponet_tc_kernel(const __grid_constant__ CUtensorMap tmW, TtcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -361,62 +378,123 @@ toponet_tc_kernel(const __grid_constant__ CUtensorMap tmW, TtcParams p) {
             }
           }
         }
-        const uint8_t* kv0 = sKV + (row & ~15) * kTtcKVStride;   // first token of this sample
-        const int sx = ((row >> 4) & 1) << 6;                    // odd samples: columns XOR 64 B
         {
+          // ---- attention of head `part` for the warp's two samples on mma.sync (16 queries x 16 keys x
+          // 32 dims per sample): q (bias added, scaled, fp16) is staged in the warp's own rows of the A
+          // buffer -- the 64 B chunk (row, h) the attention output overwrites afterwards --, k and v come
+          // straight from their smem rows through ldmatrix, P stays in registers (S fragments -> A
+          // fragments), O is normalised and stored as the out_proj A operand.
           const int h = part;
-          float2 q2[16];
           {
             uint32_t q[32];
             tmem_ld_32x32_nowait(tAcc + h * 32, q);  // in flight across the barrier
-            named_bar_sync_tokens();                 // the sample's k and v rows are in smem
+            named_bar_sync_tokens();                 // every sample's k and v rows are in smem
             tmem_ld_wait();
+            float qs[32];
+            const float4* b4 = reinterpret_cast<const float4*>(L.in_b + h * 32);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {   // torch MHA scales q by 1/sqrt(head_dim)
-              const float2 bb = __ldg(reinterpret_cast<const float2*>(L.in_b + h * 32) + i);
-              q2[i] = make_float2((__uint_as_float(q[2 * i]) + bb.x) * 0.17677669529663687f,
-                                  (__uint_as_float(q[2 * i + 1]) + bb.y) * 0.17677669529663687f);
+            for (int i = 0; i < 8; ++i) {            // torch MHA scales q by 1/sqrt(head_dim)
+              const float4 bb = __ldg(b4 + i);
+              qs[4 * i + 0] = (__uint_as_float(q[4 * i + 0]) + bb.x) * 0.17677669529663687f;
+              qs[4 * i + 1] = (__uint_as_float(q[4 * i + 1]) + bb.y) * 0.17677669529663687f;
+              qs[4 * i + 2] = (__uint_as_float(q[4 * i + 2]) + bb.z) * 0.17677669529663687f;
+              qs[4 * i + 3] = (__uint_as_float(q[4 * i + 3]) + bb.w) * 0.17677669529663687f;
+            }
+            write_a_chunk(h, qs);
+          }
+          __syncwarp();
+          const int g8 = lane >> 2, t4 = lane & 3;   // fragment coordinates: row g8 (+8), column pair t4
+          const int mi = lane >> 3, rr = lane & 7;   // ldmatrix: this lane addresses row rr of matrix mi
+          const uint32_t sA_h = smem_u32(sA) + (h >> 1) * 16384;
+#pragma unroll
+          for (int sh = 0; sh < 2; ++sh) {
+            const int r0 = quarter * 32 + sh * 16;                 // first tile row of the sample
+            const int sxs = ((r0 >> 4) & 1) << 6;                  // odd samples: k|v columns XOR 64 B
+            const uint32_t km = __shfl_sync(0xffffffffu, kmask, sh * 16);
+            // S = Q K^T : two 8-key column tiles, two 16-dim k-steps
+            float sacc[2][4];
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) sacc[nt][i] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              uint32_t qa[4], kb[4];
+              {   // matrices: (rows 0-7 | 8-15) x (dims ks*16 + 0-7 | 8-15)
+                const int qr = r0 + (mi & 1) * 8 + rr;
+                const int piece = (h & 1) * 4 + ks * 2 + (mi >> 1);
+                ttc_ldmatrix_x4(qa, sA_h + qr * 128 + ((piece ^ (qr & 7)) << 4));
+              }
+              {   // matrices: (keys 0-7 | 8-15) x (dims ks*16 + 0-7 | 8-15) -> b0, b1 of tile 0; of tile 1
+                const int kr = r0 + (mi >> 1) * 8 + rr;
+                ttc_ldmatrix_x4(kb, smem_u32(sKV) + kr * kTtcKVStride + ((h * 64) ^ sxs) +
+                                        (ks * 16 + (mi & 1) * 8) * 2);
+              }
+              ttc_mma_16816(sacc[0], qa, kb[0], kb[1]);
+              ttc_mma_16816(sacc[1], qa, kb[2], kb[3]);
+            }
+            // masked softmax of rows g8 (values [nt][0..1]) and g8 + 8 ([nt][2..3]); keys nt*8 + 2*t4 (+1)
+            float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const bool on = (km >> (nt * 8 + 2 * t4 + e)) & 1u;
+                sacc[nt][e] = on ? sacc[nt][e] : -INFINITY;
+                sacc[nt][2 + e] = on ? sacc[nt][2 + e] : -INFINITY;
+                mx0 = fmaxf(mx0, sacc[nt][e]);
+                mx1 = fmaxf(mx1, sacc[nt][2 + e]);
+              }
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+            float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                sacc[nt][e] = __expf(sacc[nt][e] - mx0);           // exp(-inf) = 0 for masked keys
+                sacc[nt][2 + e] = __expf(sacc[nt][2 + e] - mx1);
+                l0 += sacc[nt][e];
+                l1 += sacc[nt][2 + e];
+              }
+            l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+            l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+            l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+            l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+            uint32_t pa[4];
+            pa[0] = pack_half2(sacc[0][0], sacc[0][1]);
+            pa[1] = pack_half2(sacc[0][2], sacc[0][3]);
+            pa[2] = pack_half2(sacc[1][0], sacc[1][1]);
+            pa[3] = pack_half2(sacc[1][2], sacc[1][3]);
+            // O = P V : four 8-dim column tiles, one 16-key k-step
+            float oacc[4][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) oacc[j][i] = 0.f;
+#pragma unroll
+            for (int dh = 0; dh < 2; ++dh) {
+              uint32_t vb[4];   // transposed matrices: (keys 0-7 | 8-15) x (dims dh*16 + 0-7 | 8-15)
+              const int vr = r0 + (mi & 1) * 8 + rr;
+              ttc_ldmatrix_x4_trans(vb, smem_u32(sKV) + vr * kTtcKVStride + ((256 + h * 64) ^ sxs) +
+                                            (dh * 16 + (mi >> 1) * 8) * 2);
+              ttc_mma_16816(oacc[dh * 2 + 0], pa, vb[0], vb[1]);
+              ttc_mma_16816(oacc[dh * 2 + 1], pa, vb[2], vb[3]);
+            }
+            const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+            __syncwarp();                            // every lane's Q fragments of this sample are loaded
+            const int ra = r0 + g8, rb = r0 + g8 + 8;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {            // attention output columns h*32 + j*8 + 2*t4 (+1)
+              const int piece = (h & 1) * 4 + j;
+              *reinterpret_cast<uint32_t*>(sA + (h >> 1) * 16384 + ra * 128 + ((piece ^ (ra & 7)) << 4) + t4 * 4) =
+                  pack_half2(oacc[j][0] * inv0, oacc[j][1] * inv0);
+              *reinterpret_cast<uint32_t*>(sA + (h >> 1) * 16384 + rb * 128 + ((piece ^ (rb & 7)) << 4) + t4 * 4) =
+                  pack_half2(oacc[j][2] * inv1, oacc[j][3] * inv1);
             }
           }
-          float sc[16];
-          float mx = -INFINITY;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const uint8_t* kp = kv0 + j * kTtcKVStride + ((h * 64) ^ sx);
-            float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-              const uint4 u = *reinterpret_cast<const uint4*>(kp + c4 * 16);
-              const __half2* hh = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) acc = __ffma2_rn(q2[c4 * 4 + e], __half22float2(hh[e]), acc);
-            }
-            sc[j] = ((kmask >> j) & 1u) ? acc.x + acc.y : -INFINITY;
-            mx = fmaxf(mx, sc[j]);
-          }
-          float2 o2[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) o2[i] = make_float2(0.f, 0.f);
-          float lsum = 0.f;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float pj = __expf(sc[j] - mx);       // exp(-inf) = 0 for masked keys
-            lsum += pj;
-            const float2 pj2 = make_float2(pj, pj);
-            const uint8_t* vp = kv0 + j * kTtcKVStride + ((256 + h * 64) ^ sx);
-#pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-              const uint4 u = *reinterpret_cast<const uint4*>(vp + c4 * 16);
-              const __half2* hh = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) o2[c4 * 4 + e] = __ffma2_rn(pj2, __half22float2(hh[e]), o2[c4 * 4 + e]);
-            }
-          }
-          const float inv = 1.0f / lsum;
-          float o[32];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) { o[2 * i] = o2[i].x * inv; o[2 * i + 1] = o2[i].y * inv; }
-          write_a_chunk(h, o);                       // attention output columns h*32..h*32+31
         }
         tc_fence_before_sync();
         fence_proxy_async_smem();
