@@ -12,14 +12,19 @@
 //         KV buffer 66 KB k and v of the tile as fp16 rows
 //         weight ring 3 x 32 KB  the 18 [128x128] weight chunks streamed by TMA in consumption order
 // Warps: 0 = TMA producer, 1 = MMA issuer + TMEM allocator, 2..17 = 512 token threads, FOUR per token
-// (warps w, w+4, w+8, w+12 share a TMEM lane quarter): epilogues, attention on CUDA cores, LayerNorm,
-// output_proj.  Part p owns columns 32p..32p+31 = head p, and two of the eight 32-column chunks of k|v;
-// a thread keeps its 32 columns of the row in registers through a whole LayerNorm (one TMEM read, one
-// write).  LayerNorm statistics and the output dot product are combined through a small smem exchange,
-// always summed in part order.  The token work, not the GEMMs, bounds this kernel, and it is bound by
-// latency (one tile in flight per CTA, phases separated by the MMA round trips): four warps per
-// scheduler hide twice the latency of two (one -> two threads per token was 1.58x in round 1).  Key-padding semantics: masked
-// keys are excluded from the softmax; masked slots report output_proj.bias.
+// (warps w, w+4, w+8, w+12 share a TMEM lane quarter): epilogues, attention, LayerNorm, output_proj.
+// Part p owns columns 32p..32p+31 = head p, and two of the eight 32-column chunks of k|v; a thread
+// keeps its 32 columns of the row in registers through a whole LayerNorm (one TMEM read, one write).
+// LayerNorm statistics and the output dot product are combined through a small smem exchange, always
+// summed in part order.  The 16 x 16 x 32 attention of a (sample, head) is far too small for a UMMA
+// tile and runs on warp-level mma.sync: a warp owns two samples of its head; q (bias, 1/sqrt(32),
+// fp16) is staged in the warp's own rows of the A buffer, k / v fragments come from the k|v rows by
+// ldmatrix / ldmatrix.trans, softmax in fp32 on the S fragments, P (fp16) feeds the PV mma from
+// registers.  The token work, not the GEMMs, bounds this kernel, and it is bound by latency (one tile
+// in flight per CTA, phases separated by the MMA round trips): four warps per scheduler hide twice
+// the latency of two (one -> two threads per token was 1.58x in round 1, two -> four 1.34x, attention
+// on mma.sync another 1.36x).  Key-padding semantics: masked keys are excluded from
+// the softmax; masked slots report output_proj.bias.
 #pragma once
 
 #include "common.cuh"
@@ -31,7 +36,7 @@ constexpr int kTtcThreads = 576;          // 2 + 16 warps
 constexpr int kTtcTokenThreads = 512;
 constexpr int kTtcWStages = 3;
 constexpr int kTtcOffA = 0;                       // 2 k-blocks x 16 KB
-constexpr int kTtcOffKV = 32768;                  // 128 rows x 528 B (k|v fp16, padded) / x fp32 tile
+constexpr int kTtcOffKV = 32768;                  // 128 rows x 528 B (k|v fp16, padded: ldmatrix rows hit 32 banks)
 constexpr int kTtcKVStride = 528;
 constexpr int kTtcOffW = kTtcOffKV + 68608;       // 3 x 32 KB
 constexpr int kTtcOffBar = kTtcOffW + kTtcWStages * 32768;
@@ -93,8 +98,12 @@ __device__ __forceinline__ void ttc_mma_16816(float (&d)[4], const uint32_t (&a)
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__device__ __forceinline__ void named_bar_sync_tokens() {
-  asm volatile("bar.sync 1, 512;" ::: "memory");
+// Everything the token threads exchange through shared memory stays inside a TMEM lane quarter: the four
+// threads of a row (one per part) sit in the four warps of the same quarter, and a warp's two samples
+// are rows of its own quarter.  So the barriers are per quarter (ids 1..4, 128 threads each), and the
+// quarters only meet at the a_ready mbarrier of the next GEMM.
+__device__ __forceinline__ void named_bar_sync_quarter(int quarter) {
+  asm volatile("bar.sync %0, 128;" ::"r"(quarter + 1) : "memory");
 }
 
 __global__ void __launch_bounds__(kTtcThreads, 1)   // 18 warps: 5 on two of the sub-partitions -> 96 registers
@@ -218,7 +227,7 @@ toponet_tc_kernel(const __grid_constant__ CUtensorMap tmW, TtcParams p) {
     auto combine = [&](int slot, float mine) -> float {
       float* x = xch + slot * 512 + row;
       x[part * 128] = mine;
-      named_bar_sync_tokens();
+      named_bar_sync_quarter(quarter);
       return ((x[0] + x[128]) + x[256]) + x[384];
     };
     auto ldg32 = [&](const float* src, float (&v)[32]) {     // 32 consecutive floats (128 B aligned)
@@ -388,7 +397,7 @@ toponet_tc_kernel(const __grid_constant__ CUtensorMap tmW, TtcParams p) {
           {
             uint32_t q[32];
             tmem_ld_32x32_nowait(tAcc + h * 32, q);  // in flight across the barrier
-            named_bar_sync_tokens();                 // every sample's k and v rows are in smem
+            named_bar_sync_quarter(quarter);         // the k and v rows of this quarter's samples are in smem
             tmem_ld_wait();
             float qs[32];
             const float4* b4 = reinterpret_cast<const float4*>(L.in_b + h * 32);
