@@ -694,7 +694,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       if (p.trace && blockIdx.x == 0 && warp == 4 && lane == 0 && ui < 8) p.trace[120 + ui] = clock64();
       mbar_wait(&pv_done[g], static_cast<uint32_t>((bcnt + NBLK - 1) & 1));
       tc_fence_after_sync();
-      {
+      if constexpr (kWindow) {
+        // window units are bound by their latency chain: rows go straight from the registers to `out`
+        // (the transposed path below was measured 15-17 % slower here, tools/gpu/att_ab2.sh)
         const float inv = 1.0f / l_run;
         __half* op = p.out + out_tok * p.D + un.head * 64;
 #pragma unroll
@@ -714,6 +716,41 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
           }
         }
         tc_fence_before_sync();
+      } else {
+        // A row of O is 128 B = one cache line of `out`.  Stored straight from the registers, every 16 B
+        // store instruction of a warp touches 32 different lines, and the load/store unit takes one cycle
+        // per line: with 8 warps per CTA in their epilogue that is ~2 k cycles per 256-query unit.  So
+        // the row goes through the thread's own P row (swizzled, conflict-free), and the warp reads its
+        // 32 rows back transposed: 8 lanes cover one row, a store instruction touches 4 lines (global
+        // attention -9 %).  Warp-local: only the warp's own rows of the (idle) P buffer are involved.
+        const float inv = 1.0f / l_run;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r32[32];
+          tmem_ld_32x32(tO + c * 32, r32);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint4 uo;
+            uo.x = pack_half2(__uint_as_float(r32[q4 * 8 + 0]) * inv, __uint_as_float(r32[q4 * 8 + 1]) * inv);
+            uo.y = pack_half2(__uint_as_float(r32[q4 * 8 + 2]) * inv, __uint_as_float(r32[q4 * 8 + 3]) * inv);
+            uo.z = pack_half2(__uint_as_float(r32[q4 * 8 + 4]) * inv, __uint_as_float(r32[q4 * 8 + 5]) * inv);
+            uo.w = pack_half2(__uint_as_float(r32[q4 * 8 + 6]) * inv, __uint_as_float(r32[q4 * 8 + 7]) * inv);
+            *reinterpret_cast<uint4*>(myP + (((c * 4 + q4) ^ sw) << 4)) = uo;
+          }
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        const int piece = lane & 7;
+        const uint8_t* wP = sP + g * 32768 + quarter * 32 * 128;       // the warp's 32 rows
+        __half* ob = p.out + (static_cast<size_t>(un.b) * T + un.slab * 256) * p.D + un.head * 64 + piece * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = i * 4 + (lane >> 3);                           // row inside the warp
+          const int qr = g * 128 + quarter * 32 + rl;                   // row inside the unit
+          const uint4 v = *reinterpret_cast<const uint4*>(wP + rl * 128 + ((piece ^ (rl & 7)) << 4));
+          *reinterpret_cast<uint4*>(ob + static_cast<size_t>(qr) * p.D) = v;
+        }
+        __syncwarp();       // every lane has read the warp's rows: the next unit may overwrite them
       }
       if (p.trace && blockIdx.x == 0 && warp == 4 && lane == 0 && ui < 8) p.trace[136 + ui] = clock64();
       bcnt += NBLK;
